@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py — agent-steps/s of the batched warehouse env.step on N B200s, beside the CPU reference.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--steps K] [--warmup W]      # CPU arm (oracle port, all host threads)
+    torchrun --nproc-per-node N ... bench.py --gpus N ...          # one rank per GPU
+
+Workload (BASELINE.json configs[3]): WarehouseLarge, 16 agents, 262 144 envs in total, sharded
+contiguously over the GPUs (strong scaling; `--scaling weak` keeps 262 144 per GPU). A "step" is
+one `env.step` of every env: the fused move/collision/expiry/pickup/respawn/delivery kernel with
+the observation build, on int32 actions already resident in HBM (uniform-random, a pool of 8
+action tensors cycled). Observations (2.2 GB per step in total) are larger than L2, so no flush
+is needed between iterations. `e2e` is the same step through the host-buffer C ABI
+(`wh_env_step_host`): actions come from pinned host memory every step and rewards + dones go
+back to pinned host memory every step; observations stay in HBM for an on-device policy.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+VARIANT_AGENTS = {"small": 4, "medium": 9, "large": 16}
+# compulsory I/O at API dtypes + narrow state read+write, per env-step (A = R)
+ALG_BYTES_PER_ENV_STEP = {"small": 711, "medium": 3071, "large": 9147}
+SOLVER_BYTES_PER_AGENT = {"small": 85, "medium": 165, "large": 277}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--variant", default="large", choices=list(VARIANT_AGENTS))
+    ap.add_argument("--envs", type=int, default=262144, help="total envs (strong) / envs per GPU (weak)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--policy", default="random", choices=["random", "greedy", "greedy_fused"])
+    ap.add_argument("--e2e-steps", type=int, default=100)
+    ap.add_argument("--e2e-chunks", type=int, default=4)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--cpu-envs", type=int, default=8192, help="sample size (envs) of the CPU legs")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--seed", type=int, default=20261018)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (plain C restatement of the reference, pthreads over envs)
+# ------------------------------------------------------------------------------------------------
+def cpu_rollout_rate(variant, n_envs, steps, threads, seed, policy="random", warmup=5):
+    import numpy as np
+    from oracle import wh_oracle as wo
+    env = wo.OracleEnv(wo.variant_config(variant), n_envs, seed=seed)
+    env.reset()
+    rng = np.random.Generator(np.random.PCG64(seed))
+    actions = rng.integers(0, 9, size=(n_envs, env.R)).astype(np.int32)
+    env.rollout(warmup, threads, policy=policy, actions=actions)
+    t0 = time.perf_counter()
+    agent_steps = env.rollout(steps, threads, policy=policy, actions=actions)
+    dt = time.perf_counter() - t0
+    return agent_steps / dt, dt, agent_steps
+
+
+def cpu_baseline(args, budget_s):
+    threads = os.cpu_count() or 1
+    n = args.cpu_envs
+    rate, dt, _ = cpu_rollout_rate(args.variant, n, 4, threads, args.seed, "random", warmup=1)
+    steps = max(8, int(budget_s * rate / (n * VARIANT_AGENTS[args.variant])))
+    steps = min(steps, 4000)
+    rate, dt, agent_steps = cpu_rollout_rate(args.variant, n, steps, threads, args.seed, "random")
+    return {
+        "value": rate, "unit": "agent-steps/s", "cores": threads, "kind": "port",
+        "sample": f"oracle/wh_oracle.c (C port of core.py step+obs), {n} {args.variant} envs x {steps} steps, "
+                  f"random actions, {threads} pthreads, {dt:.1f}s",
+    }
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the same env.step on all host threads; each
+    step is one env.step over a bounded sample of the workload (args.cpu_envs envs)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle import wh_oracle as wo
+    threads = os.cpu_count() or 1
+    n, A = args.cpu_envs, VARIANT_AGENTS[args.variant]
+    env = wo.OracleEnv(wo.variant_config(args.variant), n, seed=args.seed)
+    env.reset()
+    rng = np.random.Generator(np.random.PCG64(args.seed))
+    actions = rng.integers(0, 9, size=(n, env.R)).astype(np.int32)
+    env.rollout(args.warmup, threads, policy="random", actions=actions)
+    t0 = time.perf_counter()
+    agent_steps = env.rollout(args.steps, threads, policy="random", actions=actions)
+    dt = time.perf_counter() - t0
+    rate = agent_steps / dt
+    sample = (f"oracle/wh_oracle.c (C port of the reference step+obs; the Python reference cannot travel to "
+              f"the GPU box), {n} {args.variant} envs per step, random actions, {threads} pthreads")
+    print(json.dumps({
+        "impl": "reference", "metric": "agent_steps_per_sec", "value": rate, "unit": "agent-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": workload_config(args, n, 1),
+        "cpu_baseline": {"value": rate, "unit": "agent-steps/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args, envs_total, world):
+    return {
+        "workload": f"warehouse-{args.variant}-{args.envs}-envs", "variant": args.variant,
+        "agents_per_env": VARIANT_AGENTS[args.variant], "envs_total": envs_total,
+        "envs_per_gpu": envs_total // world, "policy": args.policy, "episode_steps": 200,
+        "l2": "obs written per step (>= 2 GB total) exceeds L2; no flush needed",
+        "parallelism": f"env-sharded x{world}, no per-step communication",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (NVML) — runs during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.01)
+
+    def __enter__(self):
+        if self.ok:
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self.ok:
+            self.t.join()
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "NVML unavailable"}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from rllib_warehouse_b200 import VARIANTS, BatchedWarehouse
+    from rllib_warehouse_b200 import _native as nv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    A = VARIANT_AGENTS[args.variant]
+    n_local = args.envs if args.scaling == "weak" else args.envs // world
+    n_total = n_local * world
+    cfg = VARIANTS[args.variant]
+    env = BatchedWarehouse(cfg, n_local, device=dev, seed=args.seed, env_id0=rank * n_local, auto_reset=True)
+    env.reset()
+    R = env.R
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(args.seed + rank)
+    pool = [torch.randint(0, 9, (n_local, R), dtype=torch.int32, device=dev, generator=gen) for _ in range(8)]
+
+    launches_per_step = {"random": 1, "greedy": 2, "greedy_fused": 1}[args.policy]
+
+    def one_step(i):
+        if args.policy == "random":
+            env.step(pool[i & 7])
+        elif args.policy == "greedy":
+            env.step(env.greedy_actions())
+        else:
+            env.greedy_step(want_actions=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        one_step(i)
+    barrier()
+    launches0 = env.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        ev0.record()
+        for i in range(args.steps):
+            one_step(i)
+        stats = env.stats.clone()
+        if world > 1:
+            dist.all_reduce(stats)           # end-of-rollout episode statistics over NCCL
+        ev1.record()
+        barrier()
+    gpu_launches = env.launches - launches0
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = n_total * A * args.steps / (ms * 1e-3)
+
+    # ---- dominant kernel (fused step+obs) timed per launch with CUDA events on its stream ----
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(args.steps, 200))]
+    for i, (a, b) in enumerate(evs):
+        acts = pool[i & 7] if args.policy != "greedy" else env.greedy_actions()
+        a.record()
+        if args.policy == "greedy_fused":
+            env.greedy_step(want_actions=False)
+        else:
+            env.step(acts)
+        b.record()
+    torch.cuda.synchronize()
+    kms = sorted(a.elapsed_time(b) for a, b in evs)
+    k_avg_ms = sum(kms) / len(kms)
+    peaks = {}
+    peak_src = "fallback 6650 GB/s (B200_PROFILING.md)"
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak = float(peaks["hbm_gbs"])
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    except Exception:  # noqa: BLE001
+        peak = 6650.0
+    alg_bytes = ALG_BYTES_PER_ENV_STEP[args.variant] * n_local
+    achieved = alg_bytes / (k_avg_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": "wh::k_step (fused step + observation build)", "achieved": achieved,
+        "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "alg_bytes_per_launch": alg_bytes, "kernel_ms_avg": k_avg_ms, "kernel_ms_median": kms[len(kms) // 2],
+        "peak_source": peak_src,
+    }
+
+    out = {
+        "metric": "agent_steps_per_sec", "value": value, "unit": "agent-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "int32",
+        "data": "synthetic", "config": workload_config(args, n_total, world),
+        "roofline": roofline, "gpu_launches": gpu_launches, "launches_per_step": launches_per_step,
+        "clocks": clocks.summary(),
+    }
+
+    # ---- e2e through the host-buffer C ABI: pinned actions in, rewards + dones out, every step ----
+    if not args.no_e2e:
+        L = nv.lib()
+        h = C.c_void_p()
+        ccfg = nv.make_config(cfg)
+        nv.check(L.wh_env_create(C.byref(ccfg), n_local, local, rank * n_local, args.seed, args.e2e_chunks,
+                                 C.byref(h)), "wh_env_create")
+        nv.check(L.wh_env_reset(h), "wh_env_reset")
+        host_actions = [torch.randint(0, 9, (n_local, R), dtype=torch.int32).pin_memory() for _ in range(4)]
+        host_rewards = torch.zeros((n_local, R), dtype=torch.float32).pin_memory()
+        host_dones = torch.zeros(n_local, dtype=torch.uint8).pin_memory()
+        for i in range(5):
+            nv.check(L.wh_env_step_host(h, host_actions[i & 3].data_ptr(), host_rewards.data_ptr(),
+                                        host_dones.data_ptr(), None), "wh_env_step_host")
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.e2e_steps):
+            nv.check(L.wh_env_step_host(h, host_actions[i & 3].data_ptr(), host_rewards.data_ptr(),
+                                        host_dones.data_ptr(), None), "wh_env_step_host")
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        out["e2e"] = {
+            "value": n_total * A * args.e2e_steps / dt, "unit": "agent-steps/s",
+            "h2d_bytes_per_step": n_local * R * 4, "d2h_bytes_per_step": n_local * R * 4 + n_local,
+            "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps, "chunks": args.e2e_chunks,
+            "api": "wh_env_step_host (C ABI, pinned host buffers; observations stay in HBM)",
+            "reward_checksum": float(host_rewards.sum()),
+        }
+        out["gpu_launches_e2e"] = int(L.wh_env_launch_count(h))
+        L.wh_env_destroy(h)
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args, args.cpu_seconds)
+    out["stats"] = {k: v for k, v in env.stats_dict(stats).items() if not k.startswith("avg_agent_reward_") or k.endswith("_all")}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

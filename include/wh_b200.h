@@ -1,0 +1,159 @@
+/*
+ * wh_b200.h — C ABI of the B200-native batched warehouse hot path (libwh_b200.so).
+ *
+ * This is the drop-in boundary: what a maintainer of ffahleraz/rllib-warehouse would bind
+ * (ctypes) in place of the numpy bodies of
+ *     Warehouse.reset   warehouse/core.py:167-260      -> wh_reset (+ wh_build_obs, flavour 1)
+ *     Warehouse.step    warehouse/core.py:262-442      -> wh_step  (fused with the obs build)
+ *     observation dict  warehouse/core.py:224-260,371-432 -> wh_build_obs
+ *     WarehouseRandomGreedySolver.compute_action  baseline/solvers.py:27-58 -> wh_greedy
+ *     variant constants warehouse/variants.py:19-98    -> wh_config
+ * for N independent environments at once.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes only. No torch / C++ types cross this boundary.
+ *  - Layer 1 (wh_reset / wh_step / wh_build_obs / wh_greedy / wh_rollout): every data pointer is a
+ *    DEVICE pointer owned by the caller (e.g. a torch CUDA tensor); the functions launch sm_100a
+ *    kernels on `stream` (a cudaStream_t passed as void*, NULL = default stream), never allocate,
+ *    never synchronise, and return 0 or a non-zero error code (cudaError_t value, or WH_E_* below).
+ *    There is NO CPU fallback: without a CUDA device every call fails.
+ *  - Layer 2 (wh_env_*): a handle that owns device state plus pinned staging and takes HOST
+ *    buffers; it pipelines H2D actions -> kernels -> D2H rewards/dones in env chunks.
+ *  - Env-major layout: every tensor is [N, ...] with env e's record contiguous.
+ *  - Agent rows are padded to R = num_requests; rows >= num_agents[e] hold -1 in the state and
+ *    never act. Actions: 0..8 (core.py:38 MOVES), -1 = agent absent from the action dict.
+ */
+#ifndef WH_B200_H
+#define WH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WH_MAX_RACKS 8
+#define WH_NUM_STATS 80
+
+/* error codes outside the cudaError_t range */
+#define WH_E_CONFIG 10001     /* unsupported configuration (limits below) */
+#define WH_E_ARG    10002     /* NULL / inconsistent arguments */
+
+/* Limits: R <= 32, P = 4*L*L <= 64 (L <= 4), D = 4*(dim-4) <= 64 (dim <= 20), dim <= 127.
+ * All six reference variants (variants.py:19-98) are inside them. */
+typedef struct wh_config {
+    int32_t num_requests;         /* R    core.py:98  */
+    int32_t area_dimension;       /* dim  core.py:92  */
+    int32_t num_racks;            /* L    core.py:93  */
+    int32_t racks[WH_MAX_RACKS];  /*      core.py:93  */
+    int32_t episode_duration;     /*      core.py:100 */
+    int32_t pickup_wait_duration; /*      core.py:101 */
+    int32_t max_num_agents;       /*      variants.py:20,36,51 */
+    int32_t random_num_agents;    /* 1 = *Train: redraw num_agents in [1,max] on reset (variants.py:69-74) */
+} wh_config;
+
+/* Structure-of-arrays state in HBM at the narrowest width holding the reference's value range
+ * (reference: int32 everywhere, core.py:153-165). */
+typedef struct wh_state {
+    int8_t  *agent_pos;     /* [N,R,2]  (x,y)                 core.py:153 */
+    int8_t  *agent_tgt;     /* [N,R]    delivery index | -1   core.py:154 */
+    int8_t  *pickup_tgt;    /* [N,P]    delivery index | -1   core.py:158 */
+    int16_t *pickup_timer;  /* [N,P]    steps left | -1       core.py:159 */
+    int32_t *time;          /* [N]      episode_time          core.py:165 */
+    int8_t  *num_agents;    /* [N]                            core.py:95  */
+    int32_t *episode;       /* [N]      episode counter (RNG stream position), starts at -1 */
+    int32_t *acc;           /* [N,4]    per-episode {pickups, deliveries, expired, 0}, 16-byte aligned */
+} wh_state;
+
+/* One tensor per key of the observation Dict (core.py:119-148), reference dtypes, [N,R,...]. */
+typedef struct wh_obs {
+    int32_t *num_agents;             /* [N,R,1]     */
+    int32_t *self_position;          /* [N,R,2]     */
+    int8_t  *self_availability;      /* [N,R,1]     */
+    int32_t *self_delivery_target;   /* [N,R,2]     */
+    int32_t *other_positions;        /* [N,R,R-1,2] */
+    int8_t  *other_availabilities;   /* [N,R,R-1]   */
+    int32_t *other_delivery_targets; /* [N,R,R-1,2] */
+    int32_t *requests;               /* [N,R,R,4]   16-byte aligned */
+} wh_obs;
+
+#define WH_OBS_STEP  0   /* core.py:371-432 */
+#define WH_OBS_RESET 1   /* core.py:224-260 */
+
+#define WH_FLAG_AUTO_RESET 1   /* step: envs whose episode ends are reset in-kernel (native RNG) and
+                                  their observation is the first one of the next episode */
+
+/* stats vector (unsigned 64-bit counters, device memory, WH_NUM_STATS entries):
+ * [0] episodes [1] return_sum [2] pickups [3] deliveries [4] expired [5..7] reserved
+ * [8+2(n-1)] episodes with n agents, [9+2(n-1)] their return sum  (scripts/train.py:18-23) */
+
+int wh_version(void);
+const char *wh_error_string(int code);
+int wh_num_pickup_points(const wh_config *cfg);    /* core.py:96 */
+int wh_num_delivery_points(const wh_config *cfg);  /* core.py:97 */
+
+/* Warehouse.reset — core.py:167-221 (+ reset observations core.py:224-260 when obs != NULL).
+ * Replay mode (agent_pos != NULL): accepted spawn cells [N,R,2], initial request pickup ids and
+ * delivery ids [N,R] in draw order, optional num_agents [N] (the *Train redraw). Otherwise the
+ * native Philox4x32-10 stream keyed by (seed, env_id0 + e, episode) is used. env_mask [N] (u8,
+ * non-zero = reset this env) or NULL for all. */
+int wh_reset(const wh_config *cfg, const wh_state *st, int64_t n_envs, int64_t env_id0, uint64_t seed,
+             const int8_t *agent_pos, const int8_t *init_pickups, const int8_t *init_targets,
+             const int8_t *num_agents, const uint8_t *env_mask, const wh_obs *obs, void *stream);
+
+/* Warehouse.step — core.py:262-368,435-440; fused with the observation build (core.py:371-432)
+ * when obs != NULL. actions [N,R] int32; order [N,R] = agent ids in action-dict iteration order,
+ * -1 padded (NULL = ascending, core.py:279); spawn_pickups / spawn_targets [N,R] replayed respawn
+ * draws, -1 padded (NULL = native RNG); rewards [N,R] f32; dones [N] u8; stats may be NULL. */
+int wh_step(const wh_config *cfg, const wh_state *st, int64_t n_envs, int64_t env_id0, uint64_t seed,
+            const int32_t *actions, const int32_t *order,
+            const int8_t *spawn_pickups, const int8_t *spawn_targets,
+            float *rewards, uint8_t *dones, unsigned long long *stats,
+            const wh_obs *obs, int flags, void *stream);
+
+/* Observation build alone — flavour WH_OBS_STEP (core.py:371-432) or WH_OBS_RESET (core.py:224-260). */
+int wh_build_obs(const wh_config *cfg, const wh_state *st, int64_t n_envs, int flavour,
+                 const wh_obs *obs, void *stream);
+
+/* WarehouseRandomGreedySolver.compute_action — solvers.py:27-58 — on observation tensors.
+ * rand_threshold = floor(random_action_prob * 2^32). is_random / random_actions [N,R] replay the
+ * eps-random branch (solvers.py:44-45); NULL = native RNG keyed by (seed, env, episode, time, agent).
+ * actions [N,R] int32 out (-1 for rows >= num_agents). */
+int wh_greedy(const wh_config *cfg, const wh_obs *obs, const int8_t *num_agents,
+              const int32_t *episode, const int32_t *time, int64_t n_envs, int64_t env_id0,
+              uint64_t seed, uint64_t rand_threshold, const uint8_t *is_random,
+              const int32_t *random_actions, int32_t *actions, void *stream);
+
+/* run.py:42-62 loop body for all envs in ONE kernel: greedy solver evaluated from the state held
+ * in registers (identical to solving on the previous observation, incl. the reset-flavour obs at
+ * time 0) -> step -> observation build. actions_out [N,R] may be NULL. */
+int wh_greedy_step(const wh_config *cfg, const wh_state *st, int64_t n_envs, int64_t env_id0,
+                   uint64_t seed, uint64_t solver_seed, uint64_t rand_threshold,
+                   int32_t *actions_out, float *rewards, uint8_t *dones,
+                   unsigned long long *stats, const wh_obs *obs, int flags, void *stream);
+
+/* ---- Layer 2: host-buffer environment handle -------------------------------------------- */
+typedef struct wh_env wh_env;
+
+/* Allocates device state + observation tensors for n_envs on `device`, pinned staging and
+ * `n_chunks` streams. keep_obs_on_device = 1 leaves observations in HBM (wh_env_obs_ptrs). */
+int wh_env_create(const wh_config *cfg, int64_t n_envs, int device, int64_t env_id0, uint64_t seed,
+                  int n_chunks, wh_env **out);
+void wh_env_destroy(wh_env *env);
+int wh_env_reset(wh_env *env);
+/* HOST buffers: actions [N,R] int32 in; rewards [N,R] f32 and dones [N] u8 out. Copies and
+ * kernels are pipelined per env chunk; returns after everything has landed in the host buffers.
+ * obs_host (8 host pointers in wh_obs order, or NULL) additionally copies the observations out. */
+int wh_env_step_host(wh_env *env, const int32_t *actions, float *rewards, uint8_t *dones,
+                     const wh_obs *obs_host);
+/* greedy-policy variant: the solver runs on device, nothing goes H2D; rewards/dones come back. */
+int wh_env_greedy_step_host(wh_env *env, float *rewards, uint8_t *dones);
+int wh_env_obs_ptrs(wh_env *env, wh_obs *out);      /* device pointers of the resident obs */
+int wh_env_state_ptrs(wh_env *env, wh_state *out);  /* device pointers of the resident state */
+int wh_env_stats_host(wh_env *env, unsigned long long *stats_out /* [WH_NUM_STATS] */);
+int64_t wh_env_launch_count(wh_env *env);           /* kernels launched so far through this handle */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WH_B200_H */

@@ -1,0 +1,21 @@
+"""rllib_warehouse_b200 — B200-native batched implementation of the ffahleraz/rllib-warehouse
+environment step, observation build and greedy solver (hand-written sm_100a CUDA behind a C ABI).
+
+Reference-compatible surface: `Warehouse`, `WarehouseSmall/Medium/Large`, `Warehouse*Train`
+(warehouse/__init__.py:1-11), `WarehouseRandomGreedySolver` (baseline/solvers.py).
+Batched surface: `BatchedWarehouse`, `BatchedGreedySolver`.
+"""
+from .config import LARGE, MEDIUM, SMALL, VARIANTS, WarehouseConfig
+from .batched import BatchedWarehouse
+from .core import Warehouse
+from .variants import (WarehouseLarge, WarehouseLargeTrain, WarehouseMedium, WarehouseMediumTrain,
+                       WarehouseSmall, WarehouseSmallTrain)
+from .solvers import BatchedGreedySolver, WarehouseRandomGreedySolver, WarehouseSolver
+
+__all__ = [
+    "Warehouse", "WarehouseSmall", "WarehouseMedium", "WarehouseLarge",
+    "WarehouseSmallTrain", "WarehouseMediumTrain", "WarehouseLargeTrain",
+    "WarehouseConfig", "SMALL", "MEDIUM", "LARGE", "VARIANTS",
+    "BatchedWarehouse", "BatchedGreedySolver", "WarehouseRandomGreedySolver", "WarehouseSolver",
+]
+name = "rllib_warehouse_b200"

@@ -1,0 +1,212 @@
+"""BatchedWarehouse — N independent warehouse environments resident in HBM.
+
+Host-side mirror of `warehouse/core.py:73-442` for a whole batch: the same reset/step contract
+(observations, rewards, dones), but tensors of shape [N, ...] instead of per-agent dicts, and
+every bit of arithmetic done by the sm_100a kernels behind the C ABI (`include/wh_b200.h`).
+PyTorch is used only to own device memory and streams.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as nv
+from .config import WarehouseConfig
+
+OBS_KEYS = nv.OBS_KEYS
+
+
+def _dev_tensor(x, dtype, device, shape=None):
+    if x is None:
+        return None
+    if not isinstance(x, torch.Tensor):
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    x = x.to(device=device, dtype=dtype).contiguous()
+    if shape is not None:
+        x = x.reshape(shape)
+    return x
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+class BatchedWarehouse:
+    """Structure-of-arrays state + observation tensors for `num_envs` environments on one GPU.
+
+    num_agents: int (all envs) or None (= config.max_num_agents); per-env counts can be set through
+    `reset(num_agents=...)` (replay) or drawn on device when `config.random_num_agents` (*Train).
+    env_id0: global id of env 0 on this shard; the RNG is keyed by the GLOBAL env id, so results
+    do not depend on how envs are split over GPUs.
+    """
+
+    def __init__(self, config: WarehouseConfig, num_envs: int, num_agents=None, device="cuda:0",
+                 seed: int = 0, env_id0: int = 0, auto_reset: bool = False):
+        if not torch.cuda.is_available():
+            raise nv.NativeError("BatchedWarehouse needs a CUDA device: there is no CPU fallback")
+        self.lib = nv.lib()
+        self.config = config
+        self.N = int(num_envs)
+        self.R, self.P, self.D = config.num_requests, config.num_pickup_points, config.num_delivery_points
+        self.device = torch.device(device)
+        self.seed, self.env_id0 = int(seed) & (2**64 - 1), int(env_id0)
+        self.auto_reset = bool(auto_reset)
+        self._cfg = nv.make_config(config)
+        N, R, P, dev = self.N, self.R, self.P, self.device
+        A0 = config.max_num_agents if num_agents is None else int(num_agents)
+        assert 1 <= A0 <= config.max_num_agents <= R                           # core.py:89, variants.py:24
+        self.state = dict(
+            agent_pos=torch.full((N, R, 2), -1, dtype=torch.int8, device=dev),
+            agent_tgt=torch.full((N, R), -1, dtype=torch.int8, device=dev),
+            pickup_tgt=torch.full((N, P), -1, dtype=torch.int8, device=dev),
+            pickup_timer=torch.full((N, P), -1, dtype=torch.int16, device=dev),
+            time=torch.zeros(N, dtype=torch.int32, device=dev),
+            num_agents=torch.full((N,), A0, dtype=torch.int8, device=dev),
+            episode=torch.full((N,), -1, dtype=torch.int32, device=dev),
+            acc=torch.zeros((N, 4), dtype=torch.int32, device=dev),
+        )
+        i32, i8 = torch.int32, torch.int8
+        self.obs = dict(
+            num_agents=torch.zeros((N, R, 1), dtype=i32, device=dev),
+            self_position=torch.zeros((N, R, 2), dtype=i32, device=dev),
+            self_availability=torch.zeros((N, R, 1), dtype=i8, device=dev),
+            self_delivery_target=torch.zeros((N, R, 2), dtype=i32, device=dev),
+            other_positions=torch.zeros((N, R, R - 1, 2), dtype=i32, device=dev),
+            other_availabilities=torch.zeros((N, R, R - 1), dtype=i8, device=dev),
+            other_delivery_targets=torch.zeros((N, R, R - 1, 2), dtype=i32, device=dev),
+            requests=torch.zeros((N, R, R, 4), dtype=i32, device=dev),
+        )
+        self.rewards = torch.zeros((N, R), dtype=torch.float32, device=dev)
+        self.dones = torch.zeros(N, dtype=torch.uint8, device=dev)
+        self.actions = torch.full((N, R), -1, dtype=torch.int32, device=dev)
+        self.stats = torch.zeros(nv.NUM_STATS, dtype=torch.int64, device=dev)
+        self._st = nv.State(**{k: self.state[k].data_ptr() for k in nv.STATE_KEYS})
+        self._ob = nv.Obs(**{k: self.obs[k].data_ptr() for k in OBS_KEYS})
+        self.launches = 0
+
+    # ------------------------------------------------------------------------------------------
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def obs_bytes_per_env(self):
+        return sum(t[0].numel() * t.element_size() for t in self.obs.values())
+
+    # ------------------------------------------------------------------------------------------
+    def reset(self, agent_pos=None, init_pickups=None, init_targets=None, num_agents=None,
+              env_mask=None, with_obs=True):
+        """core.py:167-260. With `agent_pos` etc. the reference's recorded draws are replayed."""
+        dev, N, R = self.device, self.N, self.R
+        i8 = torch.int8
+        agent_pos = _dev_tensor(agent_pos, i8, dev, (N, R, 2))
+        init_pickups = _dev_tensor(init_pickups, i8, dev, (N, R))
+        init_targets = _dev_tensor(init_targets, i8, dev, (N, R))
+        num_agents = _dev_tensor(num_agents, i8, dev, (N,))
+        env_mask = _dev_tensor(env_mask, torch.uint8, dev, (N,))
+        keep = (agent_pos, init_pickups, init_targets, num_agents, env_mask)  # alive until launch returns
+        with torch.cuda.device(dev):
+            rc = self.lib.wh_reset(C.byref(self._cfg), C.byref(self._st), N, self.env_id0, self.seed,
+                                   _ptr(agent_pos), _ptr(init_pickups), _ptr(init_targets),
+                                   _ptr(num_agents), _ptr(env_mask),
+                                   C.byref(self._ob) if with_obs else None, self._stream())
+        nv.check(rc, "wh_reset")
+        self.launches += 1
+        del keep
+        return self.obs
+
+    def step(self, actions, order=None, spawn_pickups=None, spawn_targets=None, with_obs=True):
+        """core.py:262-442. actions [N,R] int (-1 = agent absent); order [N,R] = action-dict order."""
+        dev, N, R = self.device, self.N, self.R
+        actions = _dev_tensor(actions, torch.int32, dev, (N, R))
+        order = _dev_tensor(order, torch.int32, dev, (N, R))
+        spawn_pickups = _dev_tensor(spawn_pickups, torch.int8, dev, (N, R))
+        spawn_targets = _dev_tensor(spawn_targets, torch.int8, dev, (N, R))
+        flags = nv.FLAG_AUTO_RESET if (self.auto_reset and spawn_pickups is None) else 0
+        with torch.cuda.device(dev):
+            rc = self.lib.wh_step(C.byref(self._cfg), C.byref(self._st), N, self.env_id0, self.seed,
+                                  _ptr(actions), _ptr(order), _ptr(spawn_pickups), _ptr(spawn_targets),
+                                  self.rewards.data_ptr(), self.dones.data_ptr(), self.stats.data_ptr(),
+                                  C.byref(self._ob) if with_obs else None, flags, self._stream())
+        nv.check(rc, "wh_step")
+        self.launches += 1
+        return self.obs, self.rewards, self.dones
+
+    def greedy_step(self, random_action_prob=0.0, solver_seed=0, with_obs=True, want_actions=True):
+        """One run.py:42-62 loop iteration for all envs in a single kernel: greedy solver
+        (solvers.py:27-58) evaluated from the resident state, then step + observation build."""
+        thr = int(float(random_action_prob) * 4294967296.0)
+        flags = nv.FLAG_AUTO_RESET if self.auto_reset else 0
+        with torch.cuda.device(self.device):
+            rc = self.lib.wh_greedy_step(C.byref(self._cfg), C.byref(self._st), self.N, self.env_id0,
+                                         self.seed, int(solver_seed), thr,
+                                         self.actions.data_ptr() if want_actions else None,
+                                         self.rewards.data_ptr(), self.dones.data_ptr(),
+                                         self.stats.data_ptr(), C.byref(self._ob) if with_obs else None,
+                                         flags, self._stream())
+        nv.check(rc, "wh_greedy_step")
+        self.launches += 1
+        return self.obs, self.rewards, self.dones
+
+    def build_obs(self, flavour=nv.OBS_STEP):
+        with torch.cuda.device(self.device):
+            rc = self.lib.wh_build_obs(C.byref(self._cfg), C.byref(self._st), self.N, int(flavour),
+                                       C.byref(self._ob), self._stream())
+        nv.check(rc, "wh_build_obs")
+        self.launches += 1
+        return self.obs
+
+    def greedy_actions(self, obs=None, random_action_prob=0.0, solver_seed=0, is_random=None,
+                       random_actions=None, out=None):
+        """solvers.py:27-58 on observation tensors (defaults to the resident observations)."""
+        dev, N, R = self.device, self.N, self.R
+        if obs is None:
+            ob = self._ob
+            keep = None
+        else:
+            keep = {k: _dev_tensor(obs[k], self.obs[k].dtype, dev, self.obs[k].shape) for k in OBS_KEYS}
+            ob = nv.Obs(**{k: keep[k].data_ptr() for k in OBS_KEYS})
+        is_random = _dev_tensor(is_random, torch.uint8, dev, (N, R))
+        random_actions = _dev_tensor(random_actions, torch.int32, dev, (N, R))
+        out = self.actions if out is None else out
+        thr = int(float(random_action_prob) * 4294967296.0)
+        with torch.cuda.device(dev):
+            rc = self.lib.wh_greedy(C.byref(self._cfg), C.byref(ob), self.state["num_agents"].data_ptr(),
+                                    self.state["episode"].data_ptr(), self.state["time"].data_ptr(),
+                                    N, self.env_id0, int(solver_seed), thr, _ptr(is_random),
+                                    _ptr(random_actions), out.data_ptr(), self._stream())
+        nv.check(rc, "wh_greedy")
+        self.launches += 1
+        del keep
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    def get_state(self):
+        """State widened to the reference's int32 numpy arrays (core.py:153-165)."""
+        torch.cuda.synchronize(self.device)
+        return {k: v.to(torch.int32).cpu().numpy() for k, v in self.state.items()}
+
+    def load_state(self, **arrays):
+        """Inject state (reference widths accepted); used by tests and checkpoint restore."""
+        for k, v in arrays.items():
+            t = self.state[k]
+            t.copy_(_dev_tensor(v, t.dtype, self.device, t.shape))
+
+    def state_dict(self):
+        return {k: v.clone() for k, v in self.state.items()}
+
+    def load_state_dict(self, sd):
+        self.load_state(**sd)
+
+    def stats_dict(self, stats=None):
+        """Episode statistics (scripts/train.py:18-23 custom metrics) from the int64 stats vector."""
+        s = (self.stats if stats is None else stats).cpu().numpy().astype(np.int64)
+        out = dict(episodes=int(s[0]), return_sum=int(s[1]), pickups=int(s[2]), deliveries=int(s[3]),
+                   expired=int(s[4]))
+        tot_avg_num = 0.0
+        for n in range(1, self.R + 1):
+            ep, ret = int(s[8 + 2 * (n - 1)]), int(s[9 + 2 * (n - 1)])
+            if ep:
+                out[f"avg_agent_reward_{n}"] = ret / n / ep
+                tot_avg_num += ret / n
+        if out["episodes"]:
+            out["avg_agent_reward_all"] = tot_avg_num / out["episodes"]
+        return out

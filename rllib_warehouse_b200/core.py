@@ -1,0 +1,118 @@
+"""`Warehouse` — the reference's RLlib MultiAgentEnv surface (warehouse/core.py:73-442) on top of
+the batched CUDA environment.
+
+Same constructor signature (core.py:78-86), attributes (core.py:111-118), `reset()` and
+`step(action_dict)` contracts (per-agent observation / reward / done / info dicts keyed by
+`str(i)`, `"__all__"` in dones), so `baseline/run.py`, `scripts/train.py` and `scripts/rollout.py`
+work unchanged. One instance drives a 1-env `BatchedWarehouse`; this compatibility path pays one
+device->host copy per step and is NOT the throughput path (that is `BatchedWarehouse` /
+`WarehouseVectorEnv`, which keep everything on the GPU).
+"""
+from typing import Dict, List, Tuple
+
+import numpy as np
+
+from . import spaces
+from .batched import OBS_KEYS, BatchedWarehouse
+from .config import WarehouseConfig
+
+try:  # pragma: no cover - ray is absent in the build image
+    from ray.rllib.env.multi_agent_env import MultiAgentEnv  # type: ignore
+except Exception:  # noqa: BLE001
+    class MultiAgentEnv:  # minimal stand-in with the same role (core.py:6,73)
+        pass
+
+__all__ = ["Warehouse"]
+
+MOVES: List[List[int]] = [[x, y] for x in [-1, 0, 1] for y in [-1, 0, 1]]   # core.py:38
+PICKUP_REWARD: float = 1.0     # core.py:40
+DELIVERY_REWARD: float = 1.0   # core.py:41
+ANIMATE_FRAMES_PER_STEP: int = 10      # core.py:69
+ANIMATE_STEPS_PER_SECOND: float = 6.0  # core.py:70
+
+_DEFAULT_DEVICE = "cuda:0"
+
+
+class Warehouse(MultiAgentEnv):
+    metadata = {"render.modes": ["human"]}   # core.py:74-76
+
+    def __init__(self, num_agents: int, num_requests: int, area_dimension: int,
+                 pickup_racks_arrangement: List[int], episode_duration: int,
+                 pickup_wait_duration: int, *, device: str = None, seed: int = None,
+                 random_num_agents: bool = False, max_num_agents: int = None) -> None:
+        super().__init__()
+        assert num_agents <= num_requests                                      # core.py:89
+        self._config = WarehouseConfig(
+            num_requests, area_dimension, tuple(pickup_racks_arrangement), episode_duration,
+            pickup_wait_duration, max_num_agents or num_requests, random_num_agents)
+        # The reference draws from the process-global np.random stream (core.py:196,215,339), so
+        # `np.random.seed(s)` before construction makes it reproducible. Here the global stream
+        # only supplies the 64-bit key of the device-side counter-based generator.
+        if seed is None:
+            seed = int(np.random.randint(0, 2**31 - 1)) | (int(np.random.randint(0, 2**31 - 1)) << 31)
+        self._batched = BatchedWarehouse(self._config, 1, num_agents=num_agents,
+                                         device=device or _DEFAULT_DEVICE, seed=seed)
+        self._num_agents = num_agents
+        self._num_requests = num_requests
+        # core.py:111-118
+        self.num_agents: int = num_agents
+        self.num_requests: int = num_requests
+        self.animate_frames_per_step: int = ANIMATE_FRAMES_PER_STEP
+        self.animate_steps_per_second: float = ANIMATE_STEPS_PER_SECOND
+        self.reward_range = (0.0, 1.0)
+        self.action_space = spaces.Discrete(len(MOVES))
+        self.observation_space = spaces.observation_space(num_requests, area_dimension)
+        self._viewer = None
+
+    # ------------------------------------------------------------------------------------------
+    def _obs_dicts(self) -> Dict[str, Dict[str, np.ndarray]]:
+        host = {k: self._batched.obs[k][0].cpu().numpy() for k in OBS_KEYS}
+        A = self.num_agents
+        return {str(i): {k: host[k][i] for k in OBS_KEYS} for i in range(A)}
+
+    def reset(self) -> Dict[str, Dict[str, np.ndarray]]:
+        """core.py:167-260 (and variants.py:69-71 for random agent counts)."""
+        self._batched.reset()
+        if self._config.random_num_agents:
+            self.num_agents = self._num_agents = int(self._batched.state["num_agents"][0].item())
+        return self._obs_dicts()
+
+    def step(self, action_dict: Dict[str, int]) -> Tuple[
+            Dict[str, Dict[str, np.ndarray]], Dict[str, float], Dict[str, bool], Dict[str, Dict]]:
+        """core.py:262-442. Moves are resolved sequentially in `action_dict` iteration order
+        (core.py:279); agents missing from the dict do not move."""
+        R, A = self._num_requests, self.num_agents
+        actions = np.full((1, R), -1, np.int32)
+        order = np.full((1, R), -1, np.int32)
+        ascending = True
+        for t, (key, action) in enumerate(action_dict.items()):
+            idx = int(key)
+            action = int(action)
+            if not 0 <= idx < A:
+                raise IndexError(f"agent id {key!r} out of range")            # core.py:281
+            MOVES[action]                                                      # core.py:282 IndexError
+            actions[0, idx] = action % 9
+            order[0, t] = idx
+            ascending &= t == 0 or order[0, t - 1] < idx
+        self._batched.step(actions, order=None if ascending else order)
+        obs = self._obs_dicts()
+        rew = self._batched.rewards[0].cpu().numpy()
+        done = bool(self._batched.dones[0].item())
+        rewards = {str(i): rew[i] for i in range(A)}                            # core.py:435 (np.float32)
+        dones = {str(i): done for i in range(A)}                                # core.py:438-440
+        dones["__all__"] = done
+        return obs, rewards, dones, {str(i): {} for i in range(A)}
+
+    def render(self, mode: str = "human", animate: bool = False) -> None:
+        """core.py:444-617 draws with gym's pyglet viewer, which is not available in this image;
+        the state needed for drawing is exposed through `render_state()`."""
+        raise NotImplementedError(
+            "rendering needs gym.envs.classic_control.rendering (pyglet); use render_state() to "
+            "obtain env-0 state on the host")
+
+    def render_state(self) -> Dict[str, np.ndarray]:
+        st = self._batched.get_state()
+        A = self.num_agents
+        return dict(agent_positions=st["agent_pos"][0, :A], agent_delivery_targets=st["agent_tgt"][0, :A],
+                    pickup_point_targets=st["pickup_tgt"][0], pickup_point_timers=st["pickup_timer"][0],
+                    episode_time=int(st["time"][0]))

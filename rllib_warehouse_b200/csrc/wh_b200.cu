@@ -1,0 +1,504 @@
+// wh_b200.cu — kernels' __global__ entry points, launch dispatch and the C ABI (include/wh_b200.h).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "wh_kernels.cuh"
+
+namespace wh {
+
+constexpr int BLOCK = 256;
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+template <int G>
+struct Tile {
+    long long env, e;
+    bool live;
+    int4 *sreq;
+    __device__ __forceinline__ Tile(const KParams &P, int4 *smem) {
+        env = ((long long)blockIdx.x * BLOCK + threadIdx.x) / G;
+        live = env < P.N;
+        e = live ? env : P.N - 1;
+        sreq = smem + (threadIdx.x / G) * G;
+    }
+};
+
+// Warehouse.step (+ optional in-kernel greedy solver, + optional observation build, + optional
+// auto-reset) — core.py:262-442, solvers.py:27-58
+template <int G, int RC, bool GREEDY>
+__global__ void __launch_bounds__(BLOCK) k_step(const __grid_constant__ KParams P) {
+    __shared__ int4 smem[BLOCK];
+    const Group<G> g;
+    const Tile<G> t(P, smem);
+    const int R = RC ? RC : P.R;
+    const long long e = t.e;
+    const uint32_t env_id = (uint32_t)(P.env_id0 + e);
+    EnvRegs s;
+    load_env(P, g, e, R, s);
+
+    int act = -1, ord = -1;
+    if (GREEDY) {
+        act = greedy_from_state(P, g, R, env_id, s);
+        if (P.actions_out && t.live && g.gl < R) P.actions_out[e * R + g.gl] = act;
+    } else if (g.gl < R) {
+        act = P.actions[e * R + g.gl];
+        if (P.order) ord = P.order[e * R + g.gl];
+    }
+    s.time += 1;                                                               // core.py:267
+    do_moves<G, RC>(P, g, R, s.A, act, ord, !GREEDY && P.order != nullptr, s.pos16);
+    int acc3[3];
+    const StepOut so = do_world(P, g, e, R, env_id, s, !GREEDY && P.spawn_p != nullptr, acc3);
+    unsigned long long active = so.active;
+
+    const bool done = s.time >= P.episode;                                     // core.py:438
+    if (t.live) {
+        if (g.gl < R) P.rewards[e * R + g.gl] = so.reward;                      // core.py:435
+        if (g.gl == 0) P.dones[e] = done ? 1 : 0;
+    }
+    const bool auto_reset = (P.flags & WH_FLAG_AUTO_RESET) != 0;
+    if (g.gl == 0 && t.live) {
+        int4 a = reinterpret_cast<int4 *>(P.acc)[e];
+        a.x += acc3[0]; a.y += acc3[1]; a.z += acc3[2];
+        if (P.stats && s.time == P.episode) {                                  // train.py:18-23
+            const unsigned long long ret = (unsigned long long)(a.x + a.y);
+            atomicAdd(P.stats + 0, 1ull);
+            atomicAdd(P.stats + 1, ret);
+            atomicAdd(P.stats + 2, (unsigned long long)a.x);
+            atomicAdd(P.stats + 3, (unsigned long long)a.y);
+            atomicAdd(P.stats + 4, (unsigned long long)a.z);
+            atomicAdd(P.stats + 8 + 2 * (s.A - 1), 1ull);
+            atomicAdd(P.stats + 9 + 2 * (s.A - 1), ret);
+        }
+        if (auto_reset && done) a = make_int4(0, 0, 0, 0);
+        reinterpret_cast<int4 *>(P.acc)[e] = a;
+    }
+    int flavour = WH_OBS_STEP;
+    bool meta = false;
+    if (auto_reset && __any_sync(FULL, done)) {
+        const unsigned long long a2 = do_reset(P, g, e, R, env_id, s, false, done);
+        if (done) { active = a2; flavour = WH_OBS_RESET; }
+        meta = true;
+    }
+    if (t.live) store_env(P, g, e, R, s, meta);
+    if (P.obs.requests) build_obs<G, RC>(P, g, e, R, s, active, flavour, t.sreq, t.live);
+}
+
+// Warehouse.reset — core.py:167-260
+template <int G, int RC>
+__global__ void __launch_bounds__(BLOCK) k_reset(const __grid_constant__ KParams P) {
+    __shared__ int4 smem[BLOCK];
+    const Group<G> g;
+    const Tile<G> t(P, smem);
+    const int R = RC ? RC : P.R;
+    const long long e = t.e;
+    EnvRegs s;
+    load_env(P, g, e, R, s);
+    const bool doit = t.live && (!P.env_mask || P.env_mask[e]);
+    const unsigned long long active =
+        do_reset(P, g, e, R, (uint32_t)(P.env_id0 + e), s, P.r_agent_pos != nullptr, doit);
+    if (doit) {
+        store_env(P, g, e, R, s, true);
+        if (g.gl == 0) reinterpret_cast<int4 *>(P.acc)[e] = make_int4(0, 0, 0, 0);
+    }
+    if (P.obs.requests) build_obs<G, RC>(P, g, e, R, s, active, WH_OBS_RESET, t.sreq, doit);
+}
+
+// observation build alone — core.py:224-260 / 371-432
+template <int G, int RC>
+__global__ void __launch_bounds__(BLOCK) k_obs(const __grid_constant__ KParams P) {
+    __shared__ int4 smem[BLOCK];
+    const Group<G> g;
+    const Tile<G> t(P, smem);
+    const int R = RC ? RC : P.R;
+    EnvRegs s;
+    load_env(P, g, t.e, R, s);
+    const unsigned long long active = active_mask(g, s.pt4);
+    build_obs<G, RC>(P, g, t.e, R, s, active, P.flavour, t.sreq, t.live);
+}
+
+// WarehouseRandomGreedySolver.compute_action on observation tensors — solvers.py:27-58.
+// One group per AGENT ROW: lane r loads request r with one 128-bit load (16R contiguous bytes per
+// row), the L1 argmin with first-minimum tie-break is a single REDUX.MIN over (distance<<8 | r).
+template <int G, int RC>
+__global__ void __launch_bounds__(BLOCK) k_greedy(const __grid_constant__ KParams P) {
+    const Group<G> g;
+    const int R = RC ? RC : P.R;
+    const long long rows = P.N * R;
+    const long long row_raw = ((long long)blockIdx.x * BLOCK + threadIdx.x) / G;
+    const bool live = row_raw < rows;
+    const long long row = live ? row_raw : rows - 1;
+    const long long e = row / R;
+    const int a = (int)(row - e * R);
+    const wh_obs &o = P.obs;
+    int4 rq = make_int4(0, 0, 0, 0);
+    if (g.gl < R) rq = __ldcs(reinterpret_cast<const int4 *>(o.requests) + row * R + g.gl);
+    const int2 sp = reinterpret_cast<const int2 *>(o.self_position)[row];
+    const int2 stg = reinterpret_cast<const int2 *>(o.self_delivery_target)[row];
+    const int avail = o.self_availability[row];
+    const int A = P.g_num_agents[e];
+    const int d = abs(sp.x - rq.x) + abs(sp.y - rq.y);                         // solvers.py:54-57
+    const uint32_t key = (g.gl < R) ? (((uint32_t)d << 8) | (uint32_t)g.gl) : 0x7fffffffu;
+    const uint32_t best = __reduce_min_sync(g.gmask, key);                     // solvers.py:58 argmin
+    const uint32_t cell = g.shfl((uint32_t)(rq.x & 0xFFFF) | ((uint32_t)rq.y << 16), (int)(best & 0xFFu));
+    int tx = (int)(cell & 0xFFFF), ty = (int)(cell >> 16);
+    if (avail == 0) { tx = stg.x; ty = stg.y; }                                 // solvers.py:33-34
+    const int sx = max(-1, min(1, tx - sp.x)), sy = max(-1, min(1, ty - sp.y)); // solvers.py:41
+    int action = (sx + 1) * 3 + (sy + 1);                                      // solvers.py:47-49
+    if (P.is_random) {                                                         // solvers.py:44-45 replay
+        if (P.is_random[row]) action = P.random_actions[row];
+    } else if (P.rand_thr) {
+        uint32_t u0, u1;
+        philox4x32_10((uint32_t)(P.env_id0 + e), (uint32_t)P.g_episode[e], (uint32_t)P.g_time[e],
+                      (uint32_t)a, P.solver_seed, u0, u1);
+        if ((unsigned long long)u0 < P.rand_thr) action = (int)bounded(u1, 9u);
+    }
+    if (live && g.gl == 0) P.actions_out[row] = (a < A) ? action : -1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+struct Shape { int G, RC; };
+
+static int fill_params(const wh_config *cfg, KParams &K, Shape &sh) {
+    if (!cfg) return WH_E_ARG;
+    memset(&K, 0, sizeof(K));
+    K.R = cfg->num_requests; K.dim = cfg->area_dimension; K.L = cfg->num_racks;
+    if (K.L < 1 || K.L > WH_MAX_RACKS) return WH_E_CONFIG;
+    K.P = 4 * K.L * K.L; K.D = 4 * (K.dim - 4);
+    K.episode = cfg->episode_duration; K.wait = cfg->pickup_wait_duration;
+    K.null_pos = K.dim / 2;                                                   // core.py:107
+    K.max_agents = cfg->max_num_agents > 0 ? cfg->max_num_agents : K.R;
+    K.random_agents = cfg->random_num_agents;
+    K.regular_racks = 1;
+    for (int i = 0; i < K.L; ++i) { K.racks[i] = cfg->racks[i]; if (cfg->racks[i] != 4 * (i + 1)) K.regular_racks = 0; }
+    if (K.R < 2 || K.R > 32 || K.P > 64 || K.D > 64 || K.D < 1 || K.dim > 127 || K.R > K.P || K.R > K.D ||
+        K.max_agents > K.R || K.wait > 32767 || K.wait < 1)
+        return WH_E_CONFIG;
+    for (int i = 0; i < K.L; ++i) if (K.racks[i] < 1 || K.racks[i] >= K.dim) return WH_E_CONFIG;
+    int G = next_pow2(K.R);
+    const int gp = next_pow2((K.P + 3) / 4);
+    if (gp > G) G = gp;
+    if (G < 4) G = 4;
+    sh.G = G; sh.RC = 0;
+    if (K.R == 4 && G == 4) sh.RC = 4;
+    if (K.R == 9 && G == 16) sh.RC = 9;
+    if (K.R == 16 && G == 16) sh.RC = 16;
+    return 0;
+}
+
+static void set_state(KParams &K, const wh_state *st) {
+    K.agent_pos = st->agent_pos; K.agent_tgt = st->agent_tgt; K.pickup_tgt = st->pickup_tgt;
+    K.pickup_timer = st->pickup_timer; K.time = st->time; K.num_agents = st->num_agents;
+    K.episode_ctr = st->episode; K.acc = st->acc;
+}
+
+static bool state_ok(const wh_state *st) {
+    return st && st->agent_pos && st->agent_tgt && st->pickup_tgt && st->pickup_timer && st->time &&
+           st->num_agents && st->episode && st->acc;
+}
+
+static bool obs_ok(const wh_obs *o) {
+    return o && o->num_agents && o->self_position && o->self_availability && o->self_delivery_target &&
+           o->other_positions && o->other_availabilities && o->other_delivery_targets && o->requests;
+}
+
+enum Kind { K_STEP, K_GSTEP, K_RESET, K_OBS, K_GREEDY };
+
+template <int G, int RC>
+static void launch_kind(Kind kind, const KParams &K, long long groups, cudaStream_t s) {
+    const long long threads = groups * G;
+    const unsigned grid = (unsigned)((threads + BLOCK - 1) / BLOCK);
+    switch (kind) {
+    case K_STEP: k_step<G, RC, false><<<grid, BLOCK, 0, s>>>(K); break;
+    case K_GSTEP: k_step<G, RC, true><<<grid, BLOCK, 0, s>>>(K); break;
+    case K_RESET: k_reset<G, RC><<<grid, BLOCK, 0, s>>>(K); break;
+    case K_OBS: k_obs<G, RC><<<grid, BLOCK, 0, s>>>(K); break;
+    case K_GREEDY: k_greedy<G, RC><<<grid, BLOCK, 0, s>>>(K); break;
+    }
+}
+
+static int launch(Kind kind, const KParams &K, const Shape &sh, void *stream) {
+    if (K.N <= 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long groups = (kind == K_GREEDY) ? K.N * K.R : K.N;
+    if (sh.RC == 4) launch_kind<4, 4>(kind, K, groups, s);
+    else if (sh.RC == 9) launch_kind<16, 9>(kind, K, groups, s);
+    else if (sh.RC == 16) launch_kind<16, 16>(kind, K, groups, s);
+    else if (sh.G == 4) launch_kind<4, 0>(kind, K, groups, s);
+    else if (sh.G == 8) launch_kind<8, 0>(kind, K, groups, s);
+    else if (sh.G == 16) launch_kind<16, 0>(kind, K, groups, s);
+    else launch_kind<32, 0>(kind, K, groups, s);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace wh
+
+using namespace wh;
+
+// ---------------------------------------------------------------------------------------------
+// C ABI — layer 1
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int wh_version(void) { return 100; }
+
+const char *wh_error_string(int code) {
+    if (code == 0) return "ok";
+    if (code == WH_E_CONFIG) return "unsupported warehouse configuration (limits: 2<=R<=32, P<=64, D<=64, dim<=127)";
+    if (code == WH_E_ARG) return "NULL or inconsistent argument";
+    return cudaGetErrorString((cudaError_t)code);
+}
+
+int wh_num_pickup_points(const wh_config *cfg) { return 4 * cfg->num_racks * cfg->num_racks; }
+int wh_num_delivery_points(const wh_config *cfg) { return 4 * (cfg->area_dimension - 4); }
+
+int wh_reset(const wh_config *cfg, const wh_state *st, int64_t n_envs, int64_t env_id0, uint64_t seed,
+             const int8_t *agent_pos, const int8_t *init_pickups, const int8_t *init_targets,
+             const int8_t *num_agents, const uint8_t *env_mask, const wh_obs *obs, void *stream) {
+    KParams K; Shape sh;
+    if (int rc = fill_params(cfg, K, sh)) return rc;
+    if (!state_ok(st) || (obs && !obs_ok(obs))) return WH_E_ARG;
+    if (agent_pos && (!init_pickups || !init_targets)) return WH_E_ARG;
+    set_state(K, st);
+    if (obs) K.obs = *obs;
+    K.N = n_envs; K.env_id0 = env_id0; K.seed = seed;
+    K.r_agent_pos = agent_pos; K.r_init_p = init_pickups; K.r_init_t = init_targets;
+    K.r_num_agents = num_agents; K.env_mask = env_mask;
+    return launch(K_RESET, K, sh, stream);
+}
+
+int wh_step(const wh_config *cfg, const wh_state *st, int64_t n_envs, int64_t env_id0, uint64_t seed,
+            const int32_t *actions, const int32_t *order,
+            const int8_t *spawn_pickups, const int8_t *spawn_targets,
+            float *rewards, uint8_t *dones, unsigned long long *stats,
+            const wh_obs *obs, int flags, void *stream) {
+    KParams K; Shape sh;
+    if (int rc = fill_params(cfg, K, sh)) return rc;
+    if (!state_ok(st) || !actions || !rewards || !dones || (obs && !obs_ok(obs))) return WH_E_ARG;
+    if ((spawn_pickups == nullptr) != (spawn_targets == nullptr)) return WH_E_ARG;
+    if ((flags & WH_FLAG_AUTO_RESET) && spawn_pickups) return WH_E_ARG;  // auto-reset needs the native RNG
+    set_state(K, st);
+    if (obs) K.obs = *obs;
+    K.N = n_envs; K.env_id0 = env_id0; K.seed = seed;
+    K.actions = actions; K.order = order; K.spawn_p = spawn_pickups; K.spawn_t = spawn_targets;
+    K.rewards = rewards; K.dones = dones; K.stats = stats; K.flags = flags;
+    return launch(K_STEP, K, sh, stream);
+}
+
+int wh_greedy_step(const wh_config *cfg, const wh_state *st, int64_t n_envs, int64_t env_id0,
+                   uint64_t seed, uint64_t solver_seed, uint64_t rand_threshold,
+                   int32_t *actions_out, float *rewards, uint8_t *dones,
+                   unsigned long long *stats, const wh_obs *obs, int flags, void *stream) {
+    KParams K; Shape sh;
+    if (int rc = fill_params(cfg, K, sh)) return rc;
+    if (!state_ok(st) || !rewards || !dones || (obs && !obs_ok(obs))) return WH_E_ARG;
+    set_state(K, st);
+    if (obs) K.obs = *obs;
+    K.N = n_envs; K.env_id0 = env_id0; K.seed = seed; K.solver_seed = solver_seed;
+    K.rand_thr = rand_threshold; K.actions_out = actions_out;
+    K.rewards = rewards; K.dones = dones; K.stats = stats; K.flags = flags;
+    return launch(K_GSTEP, K, sh, stream);
+}
+
+int wh_build_obs(const wh_config *cfg, const wh_state *st, int64_t n_envs, int flavour,
+                 const wh_obs *obs, void *stream) {
+    KParams K; Shape sh;
+    if (int rc = fill_params(cfg, K, sh)) return rc;
+    if (!state_ok(st) || !obs_ok(obs) || (flavour != WH_OBS_STEP && flavour != WH_OBS_RESET)) return WH_E_ARG;
+    set_state(K, st);
+    K.obs = *obs; K.N = n_envs; K.flavour = flavour;
+    return launch(K_OBS, K, sh, stream);
+}
+
+int wh_greedy(const wh_config *cfg, const wh_obs *obs, const int8_t *num_agents,
+              const int32_t *episode, const int32_t *time, int64_t n_envs, int64_t env_id0,
+              uint64_t seed, uint64_t rand_threshold, const uint8_t *is_random,
+              const int32_t *random_actions, int32_t *actions, void *stream) {
+    KParams K; Shape sh;
+    if (int rc = fill_params(cfg, K, sh)) return rc;
+    if (!obs || !obs->requests || !obs->self_position || !obs->self_availability ||
+        !obs->self_delivery_target || !num_agents || !actions)
+        return WH_E_ARG;
+    if (is_random && !random_actions) return WH_E_ARG;
+    if (!is_random && rand_threshold && (!episode || !time)) return WH_E_ARG;
+    K.obs = *obs; K.N = n_envs; K.env_id0 = env_id0; K.solver_seed = seed; K.rand_thr = rand_threshold;
+    K.is_random = is_random; K.random_actions = random_actions; K.g_num_agents = num_agents;
+    K.g_episode = episode; K.g_time = time; K.actions_out = actions;
+    return launch(K_GREEDY, K, sh, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// C ABI — layer 2: host-buffer environment handle
+// ---------------------------------------------------------------------------------------------
+struct wh_env {
+    wh_config cfg;
+    int64_t N, env_id0;
+    uint64_t seed;
+    int device, n_chunks, R, P;
+    wh_state st;
+    wh_obs obs;
+    int32_t *d_actions;
+    float *d_rewards;
+    uint8_t *d_dones;
+    unsigned long long *d_stats;
+    cudaStream_t *streams;
+    int64_t launches;
+};
+
+#define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return (int)_e; } while (0)
+
+static wh_state offset_state(const wh_env *E, int64_t e0) {
+    wh_state s = E->st;
+    s.agent_pos += e0 * E->R * 2; s.agent_tgt += e0 * E->R; s.pickup_tgt += e0 * E->P;
+    s.pickup_timer += e0 * E->P; s.time += e0; s.num_agents += e0; s.episode += e0; s.acc += e0 * 4;
+    return s;
+}
+
+static wh_obs offset_obs(const wh_obs &b, int64_t e0, int64_t R) {
+    wh_obs o = b;
+    o.num_agents += e0 * R; o.self_position += e0 * R * 2; o.self_availability += e0 * R;
+    o.self_delivery_target += e0 * R * 2; o.other_positions += e0 * R * (R - 1) * 2;
+    o.other_availabilities += e0 * R * (R - 1); o.other_delivery_targets += e0 * R * (R - 1) * 2;
+    o.requests += e0 * R * R * 4;
+    return o;
+}
+
+int wh_env_create(const wh_config *cfg, int64_t n_envs, int device, int64_t env_id0, uint64_t seed,
+                  int n_chunks, wh_env **out) {
+    if (!cfg || !out || n_envs <= 0) return WH_E_ARG;
+    KParams K; Shape sh;
+    if (int rc = fill_params(cfg, K, sh)) return rc;
+    CK(cudaSetDevice(device));
+    wh_env *E = new (std::nothrow) wh_env();
+    if (!E) return WH_E_ARG;
+    memset(E, 0, sizeof(*E));
+    E->cfg = *cfg; E->N = n_envs; E->env_id0 = env_id0; E->seed = seed; E->device = device;
+    E->R = K.R; E->P = K.P;
+    if (n_chunks < 1) n_chunks = 1;
+    if (n_chunks > 64) n_chunks = 64;
+    E->n_chunks = n_chunks;
+    const int64_t N = n_envs, R = K.R, P = K.P;
+    CK(cudaMalloc(&E->st.agent_pos, N * R * 2)); CK(cudaMalloc(&E->st.agent_tgt, N * R));
+    CK(cudaMalloc(&E->st.pickup_tgt, N * P)); CK(cudaMalloc(&E->st.pickup_timer, N * P * 2));
+    CK(cudaMalloc(&E->st.time, N * 4)); CK(cudaMalloc(&E->st.num_agents, N));
+    CK(cudaMalloc(&E->st.episode, N * 4)); CK(cudaMalloc(&E->st.acc, N * 16));
+    CK(cudaMemset(E->st.agent_pos, 0xFF, N * R * 2)); CK(cudaMemset(E->st.agent_tgt, 0xFF, N * R));
+    CK(cudaMemset(E->st.pickup_tgt, 0xFF, N * P)); CK(cudaMemset(E->st.pickup_timer, 0xFF, N * P * 2));
+    CK(cudaMemset(E->st.time, 0, N * 4)); CK(cudaMemset(E->st.num_agents, K.max_agents, N));
+    CK(cudaMemset(E->st.episode, 0xFF, N * 4)); CK(cudaMemset(E->st.acc, 0, N * 16));
+    CK(cudaMalloc(&E->obs.num_agents, N * R * 4)); CK(cudaMalloc(&E->obs.self_position, N * R * 8));
+    CK(cudaMalloc(&E->obs.self_availability, N * R)); CK(cudaMalloc(&E->obs.self_delivery_target, N * R * 8));
+    CK(cudaMalloc(&E->obs.other_positions, N * R * (R - 1) * 8));
+    CK(cudaMalloc(&E->obs.other_availabilities, N * R * (R - 1)));
+    CK(cudaMalloc(&E->obs.other_delivery_targets, N * R * (R - 1) * 8));
+    CK(cudaMalloc(&E->obs.requests, N * R * R * 16));
+    CK(cudaMalloc(&E->d_actions, N * R * 4)); CK(cudaMalloc(&E->d_rewards, N * R * 4));
+    CK(cudaMalloc(&E->d_dones, N)); CK(cudaMalloc(&E->d_stats, WH_NUM_STATS * 8));
+    CK(cudaMemset(E->d_stats, 0, WH_NUM_STATS * 8));
+    E->streams = (cudaStream_t *)calloc((size_t)n_chunks, sizeof(cudaStream_t));
+    for (int i = 0; i < n_chunks; ++i) CK(cudaStreamCreateWithFlags(&E->streams[i], cudaStreamNonBlocking));
+    CK(cudaDeviceSynchronize());
+    *out = E;
+    return 0;
+}
+
+void wh_env_destroy(wh_env *E) {
+    if (!E) return;
+    cudaSetDevice(E->device);
+    cudaDeviceSynchronize();
+    void *ptrs[] = {E->st.agent_pos, E->st.agent_tgt, E->st.pickup_tgt, E->st.pickup_timer, E->st.time,
+                    E->st.num_agents, E->st.episode, E->st.acc, E->obs.num_agents, E->obs.self_position,
+                    E->obs.self_availability, E->obs.self_delivery_target, E->obs.other_positions,
+                    E->obs.other_availabilities, E->obs.other_delivery_targets, E->obs.requests,
+                    E->d_actions, E->d_rewards, E->d_dones, E->d_stats};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (E->streams) {
+        for (int i = 0; i < E->n_chunks; ++i) if (E->streams[i]) cudaStreamDestroy(E->streams[i]);
+        free(E->streams);
+    }
+    delete E;
+}
+
+int wh_env_reset(wh_env *E) {
+    if (!E) return WH_E_ARG;
+    CK(cudaSetDevice(E->device));
+    int rc = wh_reset(&E->cfg, &E->st, E->N, E->env_id0, E->seed, nullptr, nullptr, nullptr, nullptr,
+                      nullptr, &E->obs, E->streams[0]);
+    E->launches += 1;
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(E->streams[0]));
+    return 0;
+}
+
+static int env_step_impl(wh_env *E, const int32_t *actions, float *rewards, uint8_t *dones,
+                         const wh_obs *obs_host, bool greedy) {
+    if (!E || !rewards || !dones || (!greedy && !actions)) return WH_E_ARG;
+    CK(cudaSetDevice(E->device));
+    const int64_t R = E->R;
+    for (int c = 0; c < E->n_chunks; ++c) {
+        const int64_t e0 = E->N * c / E->n_chunks, e1 = E->N * (c + 1) / E->n_chunks, n = e1 - e0;
+        if (n <= 0) continue;
+        cudaStream_t s = E->streams[c];
+        const wh_state st = offset_state(E, e0);
+        const wh_obs ob = offset_obs(E->obs, e0, R);
+        int rc;
+        if (greedy) {
+            rc = wh_greedy_step(&E->cfg, &st, n, E->env_id0 + e0, E->seed, E->seed ^ 0x5EEDull, 0, nullptr,
+                                E->d_rewards + e0 * R, E->d_dones + e0, E->d_stats, &ob,
+                                WH_FLAG_AUTO_RESET, s);
+        } else {
+            CK(cudaMemcpyAsync(E->d_actions + e0 * R, actions + e0 * R, n * R * 4, cudaMemcpyHostToDevice, s));
+            rc = wh_step(&E->cfg, &st, n, E->env_id0 + e0, E->seed, E->d_actions + e0 * R, nullptr, nullptr,
+                         nullptr, E->d_rewards + e0 * R, E->d_dones + e0, E->d_stats, &ob,
+                         WH_FLAG_AUTO_RESET, s);
+        }
+        E->launches += 1;
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(rewards + e0 * R, E->d_rewards + e0 * R, n * R * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(dones + e0, E->d_dones + e0, n, cudaMemcpyDeviceToHost, s));
+        if (obs_host) {
+            const wh_obs oh = offset_obs(*obs_host, e0, R);
+            CK(cudaMemcpyAsync(oh.num_agents, ob.num_agents, n * R * 4, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(oh.self_position, ob.self_position, n * R * 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(oh.self_availability, ob.self_availability, n * R, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(oh.self_delivery_target, ob.self_delivery_target, n * R * 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(oh.other_positions, ob.other_positions, n * R * (R - 1) * 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(oh.other_availabilities, ob.other_availabilities, n * R * (R - 1), cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(oh.other_delivery_targets, ob.other_delivery_targets, n * R * (R - 1) * 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(oh.requests, ob.requests, n * R * R * 16, cudaMemcpyDeviceToHost, s));
+        }
+    }
+    for (int c = 0; c < E->n_chunks; ++c) CK(cudaStreamSynchronize(E->streams[c]));
+    return 0;
+}
+
+int wh_env_step_host(wh_env *E, const int32_t *actions, float *rewards, uint8_t *dones,
+                     const wh_obs *obs_host) {
+    return env_step_impl(E, actions, rewards, dones, obs_host, false);
+}
+
+int wh_env_greedy_step_host(wh_env *E, float *rewards, uint8_t *dones) {
+    return env_step_impl(E, nullptr, rewards, dones, nullptr, true);
+}
+
+int wh_env_obs_ptrs(wh_env *E, wh_obs *out) { if (!E || !out) return WH_E_ARG; *out = E->obs; return 0; }
+int wh_env_state_ptrs(wh_env *E, wh_state *out) { if (!E || !out) return WH_E_ARG; *out = E->st; return 0; }
+
+int wh_env_stats_host(wh_env *E, unsigned long long *stats_out) {
+    if (!E || !stats_out) return WH_E_ARG;
+    CK(cudaSetDevice(E->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(stats_out, E->d_stats, WH_NUM_STATS * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int64_t wh_env_launch_count(wh_env *E) { return E ? E->launches : -1; }
+
+}  // extern "C"

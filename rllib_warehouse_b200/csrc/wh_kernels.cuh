@@ -1,0 +1,551 @@
+// wh_kernels.cuh — device code of the B200-native batched warehouse hot path (sm_100a).
+//
+// Mapping: one GROUP of G lanes (G = 4/8/16/32, a power-of-two slice of a warp) owns one
+// environment; 32/G environments share a warp and run in lock-step. Within a group
+//   * lane a  (a < R) holds agent a: its cell (x | y<<8), its delivery target, its action;
+//   * lane l  holds pickup points 4l..4l+3: four int8 delivery targets packed in one 32-bit
+//     register and four timers;
+//   * lane r  (r < R) holds request r / "other agent" slot r while observations are written.
+// Everything that is per-env scalar (time, num_agents, the 64-bit active-request mask) is kept
+// redundantly in every lane of the group, so no shared memory round-trips are needed except one
+// 16-byte-per-request staging buffer used to compact the request list.
+//
+// Reference semantics (file:line into ffahleraz/rllib-warehouse) are cited at each phase.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/wh_b200.h"
+
+namespace wh {
+
+constexpr uint32_t FULL = 0xffffffffu;
+constexpr uint32_t ABSENT_MOVE = 0xffffffffu;
+constexpr uint32_t NO_CELL = 0xffff0000u;  // never equals a packed 16-bit cell
+
+// Philox counter words reserved for reset draws (step draws use c2 = episode_time >= 1)
+constexpr uint32_t CTR_NUM_AGENTS = 0xFFFFFFFFu;
+constexpr uint32_t CTR_SPAWN_AGENT = 0xF0000000u;
+constexpr uint32_t CTR_INIT_REQUESTS = 0xE0000000u;
+
+struct KParams {
+    // geometry (core.py:92-108, variants.py)
+    int R, dim, L, P, D, episode, wait, null_pos, max_agents, random_agents, regular_racks;
+    int racks[WH_MAX_RACKS];
+    // state (wh_state)
+    int8_t *agent_pos, *agent_tgt, *pickup_tgt;
+    int16_t *pickup_timer;
+    int32_t *time;
+    int8_t *num_agents;
+    int32_t *episode_ctr, *acc;
+    wh_obs obs;  // all NULL => no observation build
+    // step inputs / outputs
+    const int32_t *actions, *order;
+    const int8_t *spawn_p, *spawn_t;
+    float *rewards;
+    uint8_t *dones;
+    unsigned long long *stats;
+    int32_t *actions_out;
+    // reset replay
+    const int8_t *r_agent_pos, *r_init_p, *r_init_t, *r_num_agents;
+    const uint8_t *env_mask;
+    // solver-from-obs inputs
+    const uint8_t *is_random;
+    const int32_t *random_actions;
+    const int8_t *g_num_agents;
+    const int32_t *g_episode, *g_time;
+    long long N, env_id0;
+    unsigned long long seed, solver_seed, rand_thr;
+    int flags, flavour;
+};
+
+// ---------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              unsigned long long seed, uint32_t &o0, uint32_t &o1) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    o0 = c0; o1 = c1;
+}
+
+__device__ __forceinline__ uint32_t bounded(uint32_t u, uint32_t n) { return __umulhi(u, n); }
+
+// index of the n-th (0-based, ascending) set bit of a 64-bit mask (n < popc(mask))
+__device__ __forceinline__ int nth_set64(unsigned long long m, int n) {
+    uint32_t w = (uint32_t)m;
+    int base = 0;
+    const int c = __popc(w);
+    if (n >= c) { n -= c; w = (uint32_t)(m >> 32); base = 32; }
+    int pos = 0;
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const int cnt = __popc((w >> pos) & ((1u << s) - 1u));
+        if (n >= cnt) { n -= cnt; pos += s; }
+    }
+    return base + pos;
+}
+
+// core.py:178-188  delivery point d -> cell, v = 2 + d/4, side = d%4: (v,0) (0,v) (v,dim-1) (dim-1,v)
+__device__ __forceinline__ uint32_t delivery_cell16(int d, int dim) {
+    const int v = 2 + (d >> 2), s = d & 3;
+    const int x = (s == 1) ? 0 : (s == 3) ? dim - 1 : v;
+    const int y = (s == 0) ? 0 : (s == 2) ? dim - 1 : v;
+    return (uint32_t)x | ((uint32_t)y << 8);
+}
+
+// core.py:171-175  pickup point p -> cell: racks[p/(4L)], racks[(p/4)%L], corner p%4 in
+// (-1,-1) (0,-1) (-1,0) (0,0)
+__device__ __forceinline__ uint32_t pickup_cell16(const KParams &P, int p) {
+    const int q = p >> 2, c = p & 3;
+    const int rxi = q / P.L, ryi = q - rxi * P.L;
+    const int rx = P.regular_racks ? 4 * (rxi + 1) : P.racks[rxi];
+    const int ry = P.regular_racks ? 4 * (ryi + 1) : P.racks[ryi];
+    return (uint32_t)(rx - 1 + (c & 1)) | ((uint32_t)(ry - 1 + (c >> 1)) << 8);
+}
+
+// inverse of pickup_cell16: FIRST pickup index at cell (x,y) or -1 (core.py:319 argmax = first match)
+__device__ __forceinline__ int pickup_index(const KParams &P, int x, int y) {
+    if (P.regular_racks) {  // racks = 4,8,12,... (all reference variants)
+        const int qx = (x + 1) >> 2, ox = (x + 1) & 3, qy = (y + 1) >> 2, oy = (y + 1) & 3;
+        const bool ok = ox < 2 && oy < 2 && qx >= 1 && qx <= P.L && qy >= 1 && qy <= P.L;
+        return ok ? 4 * ((qx - 1) * P.L + (qy - 1)) + ox + 2 * oy : -1;
+    }
+    int ix = -1, iy = -1, ox = 0, oy = 0;
+    for (int i = P.L - 1; i >= 0; --i) {  // descending so that the smallest matching index wins
+        const int r = P.racks[i];
+        if (x == r - 1 || x == r) { ix = i; ox = (x == r); }
+        if (y == r - 1 || y == r) { iy = i; oy = (y == r); }
+    }
+    return (ix >= 0 && iy >= 0) ? 4 * (ix * P.L + iy) + ox + 2 * oy : -1;
+}
+
+template <int G>
+struct Group {
+    int lane, gl;        // lane in warp, lane in group
+    uint32_t gmask;      // this group's lanes within the warp
+    int gshift;          // first lane of the group
+    __device__ __forceinline__ Group() {
+        lane = threadIdx.x & 31;
+        gl = lane & (G - 1);
+        gshift = lane & ~(G - 1);
+        gmask = (G == 32 ? FULL : ((1u << G) - 1u)) << gshift;
+    }
+    __device__ __forceinline__ uint32_t ballot(bool p) const {
+        return (__ballot_sync(FULL, p) & gmask) >> gshift;
+    }
+    __device__ __forceinline__ uint32_t shfl(uint32_t v, int src) const { return __shfl_sync(FULL, v, src, G); }
+    __device__ __forceinline__ uint32_t shfl_down1(uint32_t v) const { return __shfl_down_sync(FULL, v, 1, G); }
+    __device__ __forceinline__ unsigned long long or64(unsigned long long v) const {
+        const uint32_t lo = __reduce_or_sync(gmask, (uint32_t)v);
+        uint32_t hi = 0;
+        if (4 * G > 32) hi = __reduce_or_sync(gmask, (uint32_t)(v >> 32));
+        return (unsigned long long)lo | ((unsigned long long)hi << 32);
+    }
+    __device__ __forceinline__ int add(int v) const { return (int)__reduce_add_sync(gmask, (unsigned)v); }
+};
+
+// Registers of one lane of one environment.
+struct EnvRegs {
+    uint32_t pos16;  // my agent's cell (x | y<<8), 0xFFFF for rows >= A
+    int atgt;        // my agent's delivery target or -1
+    uint32_t pt4;    // delivery targets of my 4 pickup points (0xFF = inactive)
+    int tm[4];       // their timers
+    int time, A, ep;
+};
+
+template <int G>
+__device__ __forceinline__ void load_env(const KParams &P, const Group<G> &g, long long e, int R, EnvRegs &s) {
+    s.time = P.time[e];
+    s.A = P.num_agents[e];
+    s.ep = P.episode_ctr[e];
+    s.pos16 = 0xFFFFu;
+    s.atgt = -1;
+    if (g.gl < R) {
+        s.pos16 = reinterpret_cast<const uint16_t *>(P.agent_pos)[e * R + g.gl];
+        s.atgt = P.agent_tgt[e * R + g.gl];
+    }
+    s.pt4 = 0xFFFFFFFFu;
+    s.tm[0] = s.tm[1] = s.tm[2] = s.tm[3] = -1;
+    if (4 * g.gl < P.P) {
+        s.pt4 = reinterpret_cast<const uint32_t *>(P.pickup_tgt + e * P.P)[g.gl];
+        const uint2 t = reinterpret_cast<const uint2 *>(P.pickup_timer + e * P.P)[g.gl];
+        s.tm[0] = (int16_t)(t.x & 0xFFFF); s.tm[1] = (int16_t)(t.x >> 16);
+        s.tm[2] = (int16_t)(t.y & 0xFFFF); s.tm[3] = (int16_t)(t.y >> 16);
+    }
+}
+
+template <int G>
+__device__ __forceinline__ void store_env(const KParams &P, const Group<G> &g, long long e, int R,
+                                          const EnvRegs &s, bool store_meta) {
+    if (g.gl < R) {
+        reinterpret_cast<uint16_t *>(P.agent_pos)[e * R + g.gl] = (uint16_t)s.pos16;
+        P.agent_tgt[e * R + g.gl] = (int8_t)s.atgt;
+    }
+    if (4 * g.gl < P.P) {
+        reinterpret_cast<uint32_t *>(P.pickup_tgt + e * P.P)[g.gl] = s.pt4;
+        uint2 t;
+        t.x = (uint32_t)(s.tm[0] & 0xFFFF) | ((uint32_t)(s.tm[1] & 0xFFFF) << 16);
+        t.y = (uint32_t)(s.tm[2] & 0xFFFF) | ((uint32_t)(s.tm[3] & 0xFFFF) << 16);
+        reinterpret_cast<uint2 *>(P.pickup_timer + e * P.P)[g.gl] = t;
+    }
+    if (g.gl == 0) {
+        P.time[e] = s.time;
+        if (store_meta) { P.num_agents[e] = (int8_t)s.A; P.episode_ctr[e] = s.ep; }
+    }
+}
+
+// 64-bit mask of active requests in natural pickup-index order, replicated in every lane
+template <int G>
+__device__ __forceinline__ unsigned long long active_mask(const Group<G> &g, uint32_t pt4) {
+    uint32_t nib = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) nib |= (((pt4 >> (8 * j)) & 0xFFu) != 0xFFu) ? (1u << j) : 0u;
+    const unsigned long long v = (g.gl < 16) ? ((unsigned long long)nib << (4 * g.gl)) : 0ull;
+    return g.or64(v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// S2-S3  sequential, order-dependent, collision-resolved moves — core.py:275-300
+// ---------------------------------------------------------------------------------------------
+// The reference keeps an occupancy grid and a set of forbidden (from,to) moves. Restated per lane:
+//   mark   : the cell whose occupancy bit this agent currently accounts for (NO_CELL if none).
+//            occ[c] is True  <=>  some lane has mark == c.  A successful move from p clears the
+//            mark of EVERY agent standing on p (core.py:290 clears the bit even if a co-located
+//            agent remains) and sets the mover's mark to its new cell (core.py:291).
+//   rev/ca/cb : the up-to-three moves this agent's successful move forbids (core.py:294-297):
+//            the reverse move, and for a diagonal the two crossing moves.
+// One ballot per processed agent answers "is the target marked, or is this move forbidden?".
+template <int G, int RC>
+__device__ __forceinline__ void do_moves(const KParams &P, const Group<G> &g, int R, int A,
+                                         int act, int ord, bool have_order, uint32_t &pos16) {
+    const int px = pos16 & 0xFF, py = pos16 >> 8;
+    uint32_t m = ABSENT_MOVE, rev = ABSENT_MOVE, ca = ABSENT_MOVE, cb = ABSENT_MOVE;
+    if (g.gl < A && act >= 0 && act <= 8) {
+        const int ax = (act * 11) >> 5;            // act / 3 for 0..8   (MOVES, core.py:38)
+        int x = px + ax - 1, y = py + (act - 3 * ax) - 1;
+        if ((unsigned)x >= (unsigned)P.dim) x = px;  // per-axis clamp => wall sliding (core.py:284-287)
+        if ((unsigned)y >= (unsigned)P.dim) y = py;
+        const uint32_t to = (uint32_t)x | ((uint32_t)y << 8);
+        m = pos16 | (to << 16);
+        rev = to | (pos16 << 16);                                              // core.py:294
+        ca = cb = rev;
+        if (x != px && y != py) {                                              // core.py:295-297
+            const uint32_t c1 = (uint32_t)x | ((uint32_t)py << 8), c2 = (uint32_t)px | ((uint32_t)y << 8);
+            ca = c1 | (c2 << 16);
+            cb = c2 | (c1 << 16);
+        }
+    }
+    uint32_t mark = (g.gl < A) ? pos16 : NO_CELL;   // core.py:276: every agent marks its cell
+    bool moved = false;
+    int n_order = R;
+    if (have_order) {  // entries after the first -1 are ignored
+        const uint32_t neg = g.ballot(g.gl < R && ord < 0);
+        n_order = neg ? (__ffs(neg) - 1) : R;
+    }
+    const int RR = RC ? RC : R;
+#pragma unroll
+    for (int t = 0; t < RR; ++t) {
+        int cur = t;
+        if (have_order) {
+            cur = (int)g.shfl((uint32_t)ord, t);
+            if (t >= n_order || cur >= R) cur = -1;
+        }
+        uint32_t mm = g.shfl(m, cur < 0 ? 0 : cur);
+        if (cur < 0) mm = ABSENT_MOVE;
+        const uint32_t c = mm >> 16;
+        const bool hit = (mark == c) || (moved && (rev == mm || ca == mm || cb == mm));
+        const bool ok = (g.ballot(hit) == 0u) && (mm != ABSENT_MOVE);          // core.py:289
+        if (ok) {
+            if (mark == (mm & 0xFFFFu)) mark = NO_CELL;                        // core.py:290
+            if (g.gl == cur) { mark = c; pos16 = c; moved = true; }            // core.py:291,299-300
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// S4-S8  expiry, pickups, respawn, deliveries — core.py:303-368
+// ---------------------------------------------------------------------------------------------
+struct StepOut {
+    float reward;
+    unsigned long long active;  // active-request mask after respawn
+};
+
+template <int G>
+__device__ __forceinline__ StepOut do_world(const KParams &P, const Group<G> &g, long long e, int R,
+                                            uint32_t env_id, EnvRegs &s, bool replay, int acc_out[3]) {
+    // ---- core.py:303-306 expiry (before pickup detection) ----
+    int nexp = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const bool act = ((s.pt4 >> (8 * j)) & 0xFFu) != 0xFFu;
+        s.tm[j] -= act ? 1 : 0;
+        if (s.tm[j] == 0) { s.pt4 |= 0xFFu << (8 * j); s.tm[j] = -1; ++nexp; }
+    }
+    // ---- core.py:309-335 pickups: agent on a pickup cell, free, request waiting there ----
+    const int x = s.pos16 & 0xFF, y = s.pos16 >> 8;
+    const int cand = (g.gl < s.A) ? pickup_index(P, x, y) : -1;
+    const uint32_t w = g.shfl(s.pt4, (cand < 0 ? 0 : cand) >> 2);
+    const int tg = (int)(int8_t)((w >> (8 * (cand & 3))) & 0xFFu);
+    const bool picks = cand >= 0 && s.atgt == -1 && tg > -1;
+    const unsigned long long served = g.or64(picks ? (1ull << cand) : 0ull);
+    {
+        const uint32_t nib = (g.gl < 16) ? (uint32_t)((served >> (4 * g.gl)) & 0xFull) : 0u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if ((nib >> j) & 1u) { s.pt4 |= 0xFFu << (8 * j); s.tm[j] = -1; }  // core.py:330-331
+    }
+    float reward = 0.0f;
+    if (picks) { s.atgt = tg; reward = 1.0f; }                                 // core.py:327-329,335
+    const int npick = __popc(g.ballot(picks));
+
+    // ---- core.py:338-351 respawn until exactly R requests are active ----
+    unsigned long long active = active_mask(g, s.pt4);
+    const unsigned long long pmask = (P.P >= 64) ? ~0ull : ((1ull << P.P) - 1ull);
+    int sp = -1, st_ = -1, k;
+    uint32_t up = 0, ut = 0;
+    if (replay) {
+        if (g.gl < R) { sp = P.spawn_p[e * R + g.gl]; st_ = P.spawn_t[e * R + g.gl]; }
+        const uint32_t neg = g.ballot(sp < 0);       // lanes >= R hold -1, so neg != 0 unless G == R
+        k = neg ? (__ffs(neg) - 1) : G;
+    } else {
+        k = R - __popcll(active);
+        if (k < 0) k = 0;
+        if (__any_sync(FULL, k > 0))
+            philox4x32_10(env_id, (uint32_t)s.ep, (uint32_t)s.time, (uint32_t)g.gl, P.seed, up, ut);
+    }
+    unsigned long long inactive = ~active & pmask;
+    unsigned long long avail_d = (P.D >= 64) ? ~0ull : ((1ull << P.D) - 1ull);
+    int n_inact = __popcll(inactive);
+    for (int i = 0; __any_sync(FULL, i < k); ++i) {
+        int p, d;
+        if (replay) {
+            p = (int)g.shfl((uint32_t)sp, i);
+            d = (int)g.shfl((uint32_t)st_, i);
+        } else {
+            const uint32_t a = g.shfl(up, i), b = g.shfl(ut, i);
+            const int ni = n_inact - i, di = P.D - i;
+            p = nth_set64(inactive, (int)bounded(a, (uint32_t)(ni > 0 ? ni : 1)));
+            d = nth_set64(avail_d, (int)bounded(b, (uint32_t)(di > 0 ? di : 1)));
+        }
+        if (i < k && p >= 0) {
+            inactive &= ~(1ull << p);
+            avail_d &= ~(1ull << d);
+            active |= 1ull << p;
+            if ((p >> 2) == g.gl) {                                           // core.py:344,351
+                const int j = p & 3;
+                s.pt4 = (s.pt4 & ~(0xFFu << (8 * j))) | (((uint32_t)d & 0xFFu) << (8 * j));
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) if (jj == j) s.tm[jj] = P.wait;
+            }
+        }
+    }
+    // ---- core.py:354-368 deliveries (an agent that picked up THIS step is already delivering) ----
+    bool delivered = false;
+    if (g.gl < s.A && s.atgt > -1) {
+        delivered = delivery_cell16(s.atgt, P.dim) == s.pos16;
+        if (delivered) { s.atgt = -1; reward += 1.0f; }
+    }
+    acc_out[0] = npick;
+    acc_out[1] = __popc(g.ballot(delivered));
+    acc_out[2] = g.add(nexp);
+    StepOut o;
+    o.reward = reward;
+    o.active = active;
+    return o;
+}
+
+// ---------------------------------------------------------------------------------------------
+// S9  observation build — core.py:371-432 (step flavour), core.py:224-260 (reset flavour)
+// ---------------------------------------------------------------------------------------------
+// Lane r holds padded row r of the three per-agent tables (position, availability, delivery-target
+// position) plus row r+1 (one shuffle), so "table with row a deleted" is a per-lane select. Every
+// store instruction writes one contiguous run per environment: 16R bytes (requests, 128-bit
+// stores), 8(R-1) bytes (other_*), consecutive agents a are adjacent, so each key's [R, ...] block
+// of an environment is written as one dense stream.
+template <int G, int RC>
+__device__ __forceinline__ void build_obs(const KParams &P, const Group<G> &g, long long e, int R,
+                                          const EnvRegs &s, unsigned long long active, int flavour,
+                                          int4 *sreq /* [R] staging for this group */, bool live) {
+    const int null_pos = P.null_pos;
+    const uint32_t null16 = (uint32_t)null_pos | ((uint32_t)null_pos << 8);
+    const bool real = g.gl < s.A;
+    const bool delivering = real && s.atgt > -1;
+    // core.py:372-407 padded tables (reset flavour: availability 0 and null targets, core.py:233-236)
+    const uint32_t ppos = real ? s.pos16 : null16;
+    const uint32_t avail = (flavour == WH_OBS_STEP && real && !delivering) ? 1u : 0u;
+    const uint32_t tpos = (flavour == WH_OBS_STEP && delivering) ? delivery_cell16(s.atgt, P.dim) : null16;
+    const uint32_t mine = (ppos & 0x7Fu) | (((ppos >> 8) & 0x7Fu) << 7) | ((tpos & 0x7Fu) << 14) |
+                          (((tpos >> 8) & 0x7Fu) << 21) | (avail << 28);
+    const uint32_t next = g.shfl_down1(mine);
+    const int2 my_p = make_int2(mine & 0x7F, (mine >> 7) & 0x7F), nx_p = make_int2(next & 0x7F, (next >> 7) & 0x7F);
+    const int2 my_t = make_int2((mine >> 14) & 0x7F, (mine >> 21) & 0x7F),
+               nx_t = make_int2((next >> 14) & 0x7F, (next >> 21) & 0x7F);
+    const int my_a = (mine >> 28) & 1, nx_a = (next >> 28) & 1;
+
+    // core.py:409-418 request list: active pickup points in ascending index, [px,py,dx,dy]
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int p = 4 * g.gl + j;
+        const uint32_t b = (s.pt4 >> (8 * j)) & 0xFFu;
+        if (b != 0xFFu && p < 64) {
+            const int rank = __popcll(active & ((1ull << p) - 1ull));
+            if (rank < R) {
+                const uint32_t pc = pickup_cell16(P, p), dc = delivery_cell16((int)b, P.dim);
+                sreq[rank] = make_int4(pc & 0xFF, pc >> 8, dc & 0xFF, dc >> 8);
+            }
+        }
+    }
+    __syncwarp();
+    int4 rq = make_int4(null_pos, null_pos, null_pos, null_pos);  // only if < R active (unreachable)
+    if (g.gl < R && g.gl < __popcll(active)) rq = sreq[g.gl];
+    __syncwarp();
+    if (!live) return;
+
+    const wh_obs &o = P.obs;
+    const long long row0 = e * R;
+    if (g.gl < R) {
+        o.num_agents[row0 + g.gl] = s.A;
+        reinterpret_cast<int2 *>(o.self_position)[row0 + g.gl] = my_p;
+        o.self_availability[row0 + g.gl] = (int8_t)my_a;
+        reinterpret_cast<int2 *>(o.self_delivery_target)[row0 + g.gl] = my_t;
+    }
+    int2 *op = reinterpret_cast<int2 *>(o.other_positions) + row0 * (R - 1) + g.gl;
+    int2 *ot = reinterpret_cast<int2 *>(o.other_delivery_targets) + row0 * (R - 1) + g.gl;
+    int8_t *oa = o.other_availabilities + row0 * (R - 1) + g.gl;
+    int4 *orq = reinterpret_cast<int4 *>(o.requests) + row0 * R + g.gl;
+    // core.py:428 quirk: in step() other_delivery_targets always drops row 1 (reset drops row i)
+    const int2 t_fixed = (g.gl >= 1) ? nx_t : my_t;
+    const int RR = RC ? RC : R;
+#pragma unroll
+    for (int a = 0; a < RR; ++a) {
+        if (g.gl < R - 1) {
+            const bool sh = g.gl >= a;                                          // core.py:426-427
+            __stcs(op + a * (R - 1), sh ? nx_p : my_p);
+            __stcs(oa + a * (R - 1), (int8_t)(sh ? nx_a : my_a));
+            __stcs(ot + a * (R - 1), flavour == WH_OBS_STEP ? t_fixed : (sh ? nx_t : my_t));
+        }
+        if (g.gl < R) __stcs(orq + a * R, rq);                                  // core.py:429
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// reset — core.py:167-221, variants.py:69-74
+// ---------------------------------------------------------------------------------------------
+template <int G>
+__device__ __forceinline__ unsigned long long do_reset(const KParams &P, const Group<G> &g, long long e,
+                                                       int R, uint32_t env_id, EnvRegs &s, bool replay,
+                                                       bool doit) {
+    // `doit` is uniform within the group; groups that skip still take part in warp-wide votes
+    EnvRegs n = s;
+    n.ep = s.ep + 1;
+    n.time = 0;                                                                // core.py:168
+    uint32_t u0, u1;
+    if (replay) {
+        if (P.r_num_agents) n.A = P.r_num_agents[e];
+    } else if (P.random_agents) {                                             // variants.py:70,74
+        philox4x32_10(env_id, (uint32_t)n.ep, CTR_NUM_AGENTS, 0u, P.seed, u0, u1);
+        n.A = 1 + (int)bounded(u0, (uint32_t)P.max_agents);
+    }
+    n.atgt = -1;                                                               // core.py:204
+    n.pos16 = 0xFFFFu;
+    if (replay) {
+        if (g.gl < n.A) n.pos16 = reinterpret_cast<const uint16_t *>(P.r_agent_pos)[e * R + g.gl];
+    } else {
+        // core.py:192-201 rejection sampling over [1,dim-2]^2 minus pickup cells; other agents are
+        // NOT checked, so agents may be co-located
+        bool need = doit && g.gl < n.A;
+        for (uint32_t j = 0; __any_sync(FULL, need); ++j) {
+            if (need) {
+                philox4x32_10(env_id, (uint32_t)n.ep, CTR_SPAWN_AGENT + j, (uint32_t)g.gl, P.seed, u0, u1);
+                const int x = 1 + (int)bounded(u0, (uint32_t)(P.dim - 2));
+                const int y = 1 + (int)bounded(u1, (uint32_t)(P.dim - 2));
+                if (pickup_index(P, x, y) < 0) { n.pos16 = (uint32_t)x | ((uint32_t)y << 8); need = false; }
+            }
+        }
+    }
+    n.pt4 = 0xFFFFFFFFu;                                                       // core.py:210-211
+    n.tm[0] = n.tm[1] = n.tm[2] = n.tm[3] = -1;
+    // core.py:215-221 R distinct pickup points x R distinct delivery points, paired in draw order
+    int sp = -1, st_ = -1;
+    if (replay) {
+        if (g.gl < R) { sp = P.r_init_p[e * R + g.gl]; st_ = P.r_init_t[e * R + g.gl]; }
+    } else {
+        philox4x32_10(env_id, (uint32_t)n.ep, CTR_INIT_REQUESTS, (uint32_t)g.gl, P.seed, u0, u1);
+    }
+    unsigned long long inactive = (P.P >= 64) ? ~0ull : ((1ull << P.P) - 1ull);
+    unsigned long long avail_d = (P.D >= 64) ? ~0ull : ((1ull << P.D) - 1ull);
+    unsigned long long active = 0ull;
+    for (int i = 0; i < R; ++i) {
+        int p, d;
+        if (replay) {
+            p = (int)g.shfl((uint32_t)sp, i);
+            d = (int)g.shfl((uint32_t)st_, i);
+        } else {
+            const uint32_t a = g.shfl(u0, i), b = g.shfl(u1, i);
+            p = nth_set64(inactive, (int)bounded(a, (uint32_t)(P.P - i)));
+            d = nth_set64(avail_d, (int)bounded(b, (uint32_t)(P.D - i)));
+        }
+        if (p >= 0) {
+            inactive &= ~(1ull << p);
+            avail_d &= ~(1ull << d);
+            active |= 1ull << p;
+            if ((p >> 2) == g.gl) {
+                const int j = p & 3;
+                n.pt4 = (n.pt4 & ~(0xFFu << (8 * j))) | (((uint32_t)d & 0xFFu) << (8 * j));
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) if (jj == j) n.tm[jj] = P.wait;
+            }
+        }
+    }
+    if (doit) s = n;
+    return active;
+}
+
+// ---------------------------------------------------------------------------------------------
+// greedy solver evaluated from the state in registers — baseline/solvers.py:27-58
+// ---------------------------------------------------------------------------------------------
+// Equivalent to running the solver on the observation the previous step()/reset() returned:
+// after reset (time == 0) every availability is 0 and every delivery target is the null position
+// (core.py:233-236), so agents head for the map centre; otherwise a free agent goes to the
+// L1-nearest request (first minimum in request order == ascending pickup index), a delivering
+// agent to its delivery cell.
+template <int G>
+__device__ __forceinline__ int greedy_from_state(const KParams &P, const Group<G> &g, int R,
+                                                 uint32_t env_id, const EnvRegs &s) {
+    const unsigned long long active = active_mask(g, s.pt4);
+    const int px = s.pos16 & 0xFF, py = s.pos16 >> 8;
+    // lane r takes the r-th active pickup point's cell
+    const int nact = __popcll(active);
+    uint32_t cell = (uint32_t)P.null_pos | ((uint32_t)P.null_pos << 8);
+    if (g.gl < nact && g.gl < R) cell = pickup_cell16(P, nth_set64(active, g.gl));
+    int best = 1 << 30;
+    uint32_t bcell = 0;
+    for (int r = 0; r < R; ++r) {                                              // solvers.py:53-58
+        const uint32_t c = g.shfl(cell, r);
+        const int d = abs(px - (int)(c & 0xFF)) + abs(py - (int)(c >> 8));
+        if (d < best) { best = d; bcell = c; }
+    }
+    uint32_t target;
+    const bool free_agent = s.time > 0 && s.atgt == -1;                        // availability 1
+    if (free_agent) target = bcell;
+    else if (s.time > 0) target = delivery_cell16(s.atgt, P.dim);              // solvers.py:33-34
+    else target = (uint32_t)P.null_pos | ((uint32_t)P.null_pos << 8);
+    const int sx = max(-1, min(1, (int)(target & 0xFF) - px));                 // solvers.py:41
+    const int sy = max(-1, min(1, (int)(target >> 8) - py));
+    int action = (sx + 1) * 3 + (sy + 1);                                      // solvers.py:47-49
+    if (P.rand_thr) {                                                          // solvers.py:44-45
+        uint32_t u0, u1;
+        philox4x32_10(env_id, (uint32_t)s.ep, (uint32_t)s.time, (uint32_t)g.gl, P.solver_seed, u0, u1);
+        if ((unsigned long long)u0 < P.rand_thr) action = (int)bounded(u1, 9u);
+    }
+    return (g.gl < s.A) ? action : -1;
+}
+
+}  // namespace wh

@@ -1,0 +1,55 @@
+"""Multi-GPU plumbing: envs shard trivially (no per-step communication). One process per GPU;
+the only collective is the end-of-rollout all-reduce of the int64 episode-statistics vector
+(NCCL over NVLink on GPUs; gloo in the CPU tests). Rewards are integer-valued, so integer sums
+are exact and independent of reduction order."""
+import os
+
+import torch
+import torch.distributed as dist
+
+from . import _native as nv
+
+
+def shard_range(num_envs_total: int, rank: int, world: int):
+    """Contiguous global env-id range [lo, hi) of `rank`. The RNG is keyed by the GLOBAL env id
+    (wh_config / env_id0), so per-env results do not depend on `world`."""
+    lo = num_envs_total * rank // world
+    hi = num_envs_total * (rank + 1) // world
+    return lo, hi
+
+
+def init_from_env(backend=None, device=None):
+    """Reads RANK / WORLD_SIZE / MASTER_* (torchrun contract). Returns (rank, world)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kw = {"device_id": device} if (backend == "nccl" and device is not None) else {}
+        dist.init_process_group(backend, **kw)
+    return rank, world
+
+
+def allreduce_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum of the per-shard statistics vectors (layout: include/wh_b200.h). Returns a new tensor."""
+    assert stats.dtype == torch.int64 and stats.numel() == nv.NUM_STATS
+    out = stats.clone()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+    return out
+
+
+def stats_to_metrics(stats, max_agents: int):
+    """The reference's episode metrics (scripts/train.py:18-23): avg_agent_reward_all and
+    avg_agent_reward_{n} from the reduced vector."""
+    s = [int(v) for v in stats.tolist()]
+    out = dict(episodes=s[0], return_sum=s[1], pickups=s[2], deliveries=s[3], expired=s[4])
+    num = 0.0
+    for n in range(1, max_agents + 1):
+        ep, ret = s[8 + 2 * (n - 1)], s[9 + 2 * (n - 1)]
+        if ep:
+            out[f"avg_agent_reward_{n}"] = ret / n / ep
+            num += ret / n
+    if s[0]:
+        out["avg_agent_reward_all"] = num / s[0]
+    return out

@@ -1,0 +1,122 @@
+"""CPU-side checks: the C-ABI library loads and exports every declared symbol, argument/config
+validation happens before any CUDA call, host-side helpers, and the N>1 statistics reduction over
+gloo (world_size 2)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from rllib_warehouse_b200 import _native as nv
+    L = nv.lib()
+    header = open(os.path.join(ROOT, "include", "wh_b200.h")).read()
+    declared = set(re.findall(r"\b(wh_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(nv.SYMBOLS), declared ^ set(nv.SYMBOLS)
+    for s in declared:
+        assert hasattr(L, s), s
+    assert L.wh_version() >= 100
+    assert L.wh_error_string(0) == b"ok"
+
+
+def test_config_and_argument_validation_needs_no_gpu():
+    from rllib_warehouse_b200 import LARGE, WarehouseConfig
+    from rllib_warehouse_b200 import _native as nv
+    L = nv.lib()
+    cfg = nv.make_config(LARGE)
+    assert L.wh_num_pickup_points(C.byref(cfg)) == 64 and L.wh_num_delivery_points(C.byref(cfg)) == 64
+    st, ob = nv.State(), nv.Obs()
+    # NULL state pointers -> WH_E_ARG, no launch
+    assert L.wh_step(C.byref(cfg), C.byref(st), 4, 0, 0, None, None, None, None, None, None, None, None, 0, None) == 10002
+    assert L.wh_build_obs(C.byref(cfg), C.byref(st), 4, 0, C.byref(ob), None) == 10002
+    # unsupported geometry -> WH_E_CONFIG
+    bad = nv.make_config(WarehouseConfig(16, 40, (4, 8, 12, 16)))      # D = 144 > 64
+    assert L.wh_reset(C.byref(bad), C.byref(st), 4, 0, 0, None, None, None, None, None, None, None) == 10001
+    bad = nv.make_config(WarehouseConfig(40, 20, (4, 8, 12, 16)))      # R > 32
+    assert L.wh_reset(C.byref(bad), C.byref(st), 4, 0, 0, None, None, None, None, None, None, None) == 10001
+    assert b"unsupported" in L.wh_error_string(10001)
+
+
+def test_no_cpu_fallback():
+    from rllib_warehouse_b200 import SMALL, BatchedWarehouse
+    from rllib_warehouse_b200 import _native as nv
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(nv.NativeError):
+        BatchedWarehouse(SMALL, 4)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "rllib_warehouse_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("the oracle", "").lower() or f == "build.py", (dirpath, f)
+
+
+def test_spaces_and_variant_constants():
+    from rllib_warehouse_b200 import LARGE, MEDIUM, SMALL, spaces
+    assert (SMALL.num_pickup_points, SMALL.num_delivery_points, SMALL.null_position) == (16, 32, 6)
+    assert (MEDIUM.num_pickup_points, MEDIUM.num_delivery_points, MEDIUM.null_position) == (36, 48, 8)
+    assert (LARGE.num_pickup_points, LARGE.num_delivery_points, LARGE.null_position) == (64, 64, 10)
+    sp = spaces.observation_space(4, 12)
+    ob = {"num_agents": np.array([3], np.int32), "self_position": np.array([1, 2], np.int32),
+          "self_availability": np.array([1], np.int8), "self_delivery_target": np.array([6, 6], np.int32),
+          "other_positions": np.zeros((3, 2), np.int32), "other_availabilities": np.zeros(3, np.int8),
+          "other_delivery_targets": np.zeros((3, 2), np.int32), "requests": np.zeros((4, 4), np.int32)}
+    assert sp.contains(ob)
+    ob["self_position"] = np.array([1, 13], np.int32)
+    assert not sp.contains(ob)
+    assert spaces.Discrete(9).contains(8) and not spaces.Discrete(9).contains(9)
+
+
+def test_shard_range_covers_everything():
+    from rllib_warehouse_b200.parallel import shard_range
+    for n, w in [(262144, 8), (1000, 3), (5, 8)]:
+        r = [shard_range(n, k, w) for k in range(w)]
+        assert r[0][0] == 0 and r[-1][1] == n and all(r[i][1] == r[i + 1][0] for i in range(w - 1))
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from rllib_warehouse_b200 import _native as nv
+    from rllib_warehouse_b200.parallel import allreduce_stats, shard_range, stats_to_metrics
+    from oracle import wh_oracle as wo
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    n_total = 64
+    lo, hi = shard_range(n_total, rank, world)
+    env = wo.OracleEnv(wo.variant_config("small", random_num_agents=True), hi - lo, seed=11, env_id0=lo)
+    env.reset()
+    env.rollout(200, 1, policy="greedy", auto_reset=True)
+    local = torch.from_numpy(env.stats.copy())
+    total = allreduce_stats(local)
+    q.put((rank, total.tolist(), stats_to_metrics(total, 4)))
+    dist.destroy_process_group()
+
+
+def test_stats_allreduce_gloo_world2():
+    """Sharded rollout on 2 ranks (CPU stand-in for the per-GPU shards) + all-reduce == 1 rank."""
+    import torch.multiprocessing as mp
+    from oracle import wh_oracle as wo
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    whole = wo.OracleEnv(wo.variant_config("small", random_num_agents=True), 64, seed=11)
+    whole.reset()
+    whole.rollout(200, 1, policy="greedy", auto_reset=True)
+    for _, tot, metrics in res:
+        assert tot == whole.stats.tolist()
+        assert metrics["episodes"] == 64 and "avg_agent_reward_all" in metrics
