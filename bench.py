@@ -8,8 +8,8 @@
 Workload (BASELINE.json configs[3]): WarehouseLarge, 16 agents, 262 144 envs in total, sharded
 contiguously over the GPUs (strong scaling; `--scaling weak` keeps 262 144 per GPU). A "step" is
 one `env.step` of every env: the fused move/collision/expiry/pickup/respawn/delivery kernel with
-the observation build, on int32 actions already resident in HBM (uniform-random, a pool of 8
-action tensors cycled). Observations (2.2 GB per step in total) are larger than L2, so no flush
+the observation build, on int32 actions already resident in HBM (uniform-random; a pool of 200
+action tensors = one full episode of distinct actions, cycled). Observations (2.2 GB per step in total) are larger than L2, so no flush
 is needed between iterations. `e2e` is the same step through the host-buffer C ABI
 (`wh_env_step_host`): actions come from pinned host memory every step and rewards + dones go
 back to pinned host memory every step; observations stay in HBM for an on-device policy.
@@ -204,13 +204,14 @@ def run_b200(args):
     R = env.R
     gen = torch.Generator(device=dev)
     gen.manual_seed(args.seed + rank)
-    pool = [torch.randint(0, 9, (n_local, R), dtype=torch.int32, device=dev, generator=gen) for _ in range(8)]
+    n_pool = 200 if args.policy == "random" else 1
+    pool = [torch.randint(0, 9, (n_local, R), dtype=torch.int32, device=dev, generator=gen) for _ in range(n_pool)]
 
     launches_per_step = {"random": 1, "greedy": 2, "greedy_fused": 1}[args.policy]
 
     def one_step(i):
         if args.policy == "random":
-            env.step(pool[i & 7])
+            env.step(pool[i % n_pool])
         elif args.policy == "greedy":
             env.step(env.greedy_actions())
         else:
@@ -246,7 +247,7 @@ def run_b200(args):
     # ---- dominant kernel (fused step+obs) timed per launch with CUDA events on its stream ----
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(args.steps, 200))]
     for i, (a, b) in enumerate(evs):
-        acts = pool[i & 7] if args.policy != "greedy" else env.greedy_actions()
+        acts = pool[i % n_pool] if args.policy != "greedy" else env.greedy_actions()
         a.record()
         if args.policy == "greedy_fused":
             env.greedy_step(want_actions=False)

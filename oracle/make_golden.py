@@ -27,12 +27,32 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.environ.get("WH_REFERENCE", "/root/reference")
-sys.path.insert(0, os.path.join(HERE, "stubs"))
-sys.path.insert(0, REF)
-sys.path.insert(0, os.path.join(REF, "baseline"))
 
-import warehouse as refwh  # noqa: E402  (the reference package)
-from solvers import WarehouseRandomGreedySolver  # noqa: E402  (reference baseline/solvers.py)
+
+def _import_reference():
+    """Imports the reference's `warehouse` package and `baseline/solvers.py` under the stub
+    gym/ray WITHOUT leaving them in sys.modules / sys.path: this repo ships its own `warehouse`
+    and `solvers` modules under the same names (the drop-in shims), and the two must not shadow
+    each other inside one test process."""
+    names = ("warehouse", "solvers", "gym", "ray")
+    mine = lambda k: k in names or k.startswith(tuple(n + "." for n in names))
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if mine(k)}
+    paths = [os.path.join(HERE, "stubs"), REF, os.path.join(REF, "baseline")]
+    sys.path[:0] = paths
+    try:
+        import warehouse as ref_pkg
+        from solvers import WarehouseRandomGreedySolver as ref_solver
+        assert os.path.realpath(ref_pkg.__file__).startswith(os.path.realpath(REF)), ref_pkg.__file__
+    finally:
+        for p in paths:
+            sys.path.remove(p)
+        for k in [k for k in sys.modules if mine(k)]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+    return ref_pkg, ref_solver
+
+
+refwh, WarehouseRandomGreedySolver = _import_reference()
 
 OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
 

@@ -14,26 +14,25 @@ constexpr int BLOCK = 256;
 // ---------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------
-template <int G>
+// Which environment a lane works for: warp w of the grid owns envs [w*epw, (w+1)*epw).
+template <int GC>
 struct Tile {
     long long env, e;
     bool live;
-    int4 *sreq;
-    __device__ __forceinline__ Tile(const KParams &P, int4 *smem) {
-        env = ((long long)blockIdx.x * BLOCK + threadIdx.x) / G;
-        live = env < P.N;
-        e = live ? env : P.N - 1;
-        sreq = smem + (threadIdx.x / G) * G;
+    __device__ __forceinline__ Tile(const KParams &P, const Group<GC> &g) {
+        const long long warp = ((long long)blockIdx.x * BLOCK + threadIdx.x) >> 5;
+        env = warp * g.epw + g.gi;
+        live = !g.ghost && env < P.N;
+        e = (env < P.N) ? env : P.N - 1;   // dead lanes shadow a valid env so that loads stay in bounds
     }
 };
 
 // Warehouse.step (+ optional in-kernel greedy solver, + optional observation build, + optional
 // auto-reset) — core.py:262-442, solvers.py:27-58
-template <int G, int RC, bool GREEDY>
+template <int GC, int RC, bool GREEDY>
 __global__ void __launch_bounds__(BLOCK) k_step(const __grid_constant__ KParams P) {
-    __shared__ int4 smem[BLOCK];
-    const Group<G> g;
-    const Tile<G> t(P, smem);
+    const Group<GC> g(P.G);
+    const Tile<GC> t(P, g);
     const int R = RC ? RC : P.R;
     const long long e = t.e;
     const uint32_t env_id = (uint32_t)(P.env_id0 + e);
@@ -42,17 +41,17 @@ __global__ void __launch_bounds__(BLOCK) k_step(const __grid_constant__ KParams 
 
     int act = -1, ord = -1;
     if (GREEDY) {
-        act = greedy_from_state(P, g, R, env_id, s);
+        act = greedy_from_state<GC, RC>(P, g, R, env_id, s);
         if (P.actions_out && t.live && g.gl < R) P.actions_out[e * R + g.gl] = act;
     } else if (g.gl < R) {
         act = P.actions[e * R + g.gl];
         if (P.order) ord = P.order[e * R + g.gl];
     }
     s.time += 1;                                                               // core.py:267
-    do_moves<G, RC>(P, g, R, s.A, act, ord, !GREEDY && P.order != nullptr, s.pos16);
-    int acc3[3];
-    const StepOut so = do_world(P, g, e, R, env_id, s, !GREEDY && P.spawn_p != nullptr, acc3);
+    do_moves<GC, RC>(P, g, R, s.A, act, ord, !GREEDY && P.order != nullptr, s.pos16);
+    const StepOut so = do_world(P, g, e, R, env_id, s, !GREEDY && P.spawn_p != nullptr);
     unsigned long long active = so.active;
+    uint32_t tpos16 = so.tpos16;
 
     const bool done = s.time >= P.episode;                                     // core.py:438
     if (t.live) {
@@ -60,10 +59,11 @@ __global__ void __launch_bounds__(BLOCK) k_step(const __grid_constant__ KParams 
         if (g.gl == 0) P.dones[e] = done ? 1 : 0;
     }
     const bool auto_reset = (P.flags & WH_FLAG_AUTO_RESET) != 0;
-    if (g.gl == 0 && t.live) {
+    const bool flush = s.time == P.episode;
+    if (g.gl == 0 && t.live && ((so.npick | so.ndeliv | so.nexp) != 0 || flush || (auto_reset && done))) {
         int4 a = reinterpret_cast<int4 *>(P.acc)[e];
-        a.x += acc3[0]; a.y += acc3[1]; a.z += acc3[2];
-        if (P.stats && s.time == P.episode) {                                  // train.py:18-23
+        a.x += so.npick; a.y += so.ndeliv; a.z += so.nexp;
+        if (P.stats && flush) {                                                // train.py:18-23
             const unsigned long long ret = (unsigned long long)(a.x + a.y);
             atomicAdd(P.stats + 0, 1ull);
             atomicAdd(P.stats + 1, ret);
@@ -79,20 +79,19 @@ __global__ void __launch_bounds__(BLOCK) k_step(const __grid_constant__ KParams 
     int flavour = WH_OBS_STEP;
     bool meta = false;
     if (auto_reset && __any_sync(FULL, done)) {
-        const unsigned long long a2 = do_reset(P, g, e, R, env_id, s, false, done);
+        const unsigned long long a2 = do_reset(P, g, e, R, env_id, s, false, done && t.live);
         if (done) { active = a2; flavour = WH_OBS_RESET; }
         meta = true;
     }
     if (t.live) store_env(P, g, e, R, s, meta);
-    if (P.obs.requests) build_obs<G, RC>(P, g, e, R, s, active, flavour, t.sreq, t.live);
+    if (P.obs.requests) build_obs<GC, RC>(P, g, e, R, s, active, tpos16, flavour, t.live);
 }
 
 // Warehouse.reset — core.py:167-260
-template <int G, int RC>
+template <int GC, int RC>
 __global__ void __launch_bounds__(BLOCK) k_reset(const __grid_constant__ KParams P) {
-    __shared__ int4 smem[BLOCK];
-    const Group<G> g;
-    const Tile<G> t(P, smem);
+    const Group<GC> g(P.G);
+    const Tile<GC> t(P, g);
     const int R = RC ? RC : P.R;
     const long long e = t.e;
     EnvRegs s;
@@ -104,45 +103,44 @@ __global__ void __launch_bounds__(BLOCK) k_reset(const __grid_constant__ KParams
         store_env(P, g, e, R, s, true);
         if (g.gl == 0) reinterpret_cast<int4 *>(P.acc)[e] = make_int4(0, 0, 0, 0);
     }
-    if (P.obs.requests) build_obs<G, RC>(P, g, e, R, s, active, WH_OBS_RESET, t.sreq, doit);
+    if (P.obs.requests) build_obs<GC, RC>(P, g, e, R, s, active, 0u, WH_OBS_RESET, doit);
 }
 
 // observation build alone — core.py:224-260 / 371-432
-template <int G, int RC>
+template <int GC, int RC>
 __global__ void __launch_bounds__(BLOCK) k_obs(const __grid_constant__ KParams P) {
-    __shared__ int4 smem[BLOCK];
-    const Group<G> g;
-    const Tile<G> t(P, smem);
+    const Group<GC> g(P.G);
+    const Tile<GC> t(P, g);
     const int R = RC ? RC : P.R;
     EnvRegs s;
     load_env(P, g, t.e, R, s);
     const unsigned long long active = active_mask(g, s.pt4);
-    build_obs<G, RC>(P, g, t.e, R, s, active, P.flavour, t.sreq, t.live);
+    build_obs<GC, RC>(P, g, t.e, R, s, active, target_cell16(P, s.atgt), P.flavour, t.live);
 }
 
 // WarehouseRandomGreedySolver.compute_action on observation tensors — solvers.py:27-58.
-// One group per AGENT ROW: lane r loads request r with one 128-bit load (16R contiguous bytes per
-// row), the L1 argmin with first-minimum tie-break is a single REDUX.MIN over (distance<<8 | r).
-template <int G, int RC>
+// One group of R lanes per AGENT ROW: lane r loads request r with one 128-bit load (16R contiguous
+// bytes per row); the L1 argmin with first-minimum tie-break is a min-reduction over
+// (distance<<8 | r) inside the group.
+template <int RC>
 __global__ void __launch_bounds__(BLOCK) k_greedy(const __grid_constant__ KParams P) {
-    const Group<G> g;
     const int R = RC ? RC : P.R;
+    const Group<RC> g(R);
     const long long rows = P.N * R;
-    const long long row_raw = ((long long)blockIdx.x * BLOCK + threadIdx.x) / G;
-    const bool live = row_raw < rows;
-    const long long row = live ? row_raw : rows - 1;
+    const long long warp = ((long long)blockIdx.x * BLOCK + threadIdx.x) >> 5;
+    const long long row_raw = warp * g.epw + g.gi;
+    const bool live = !g.ghost && row_raw < rows;
+    const long long row = row_raw < rows ? row_raw : rows - 1;
     const long long e = row / R;
     const int a = (int)(row - e * R);
     const wh_obs &o = P.obs;
-    int4 rq = make_int4(0, 0, 0, 0);
-    if (g.gl < R) rq = __ldcs(reinterpret_cast<const int4 *>(o.requests) + row * R + g.gl);
+    const int4 rq = __ldcs(reinterpret_cast<const int4 *>(o.requests) + row * R + g.gl);
     const int2 sp = reinterpret_cast<const int2 *>(o.self_position)[row];
     const int2 stg = reinterpret_cast<const int2 *>(o.self_delivery_target)[row];
     const int avail = o.self_availability[row];
     const int A = P.g_num_agents[e];
     const int d = abs(sp.x - rq.x) + abs(sp.y - rq.y);                         // solvers.py:54-57
-    const uint32_t key = (g.gl < R) ? (((uint32_t)d << 8) | (uint32_t)g.gl) : 0x7fffffffu;
-    const uint32_t best = __reduce_min_sync(g.gmask, key);                     // solvers.py:58 argmin
+    const uint32_t best = g.min_u32(((uint32_t)d << 8) | (uint32_t)g.gl);      // solvers.py:58 argmin
     const uint32_t cell = g.shfl((uint32_t)(rq.x & 0xFFFF) | ((uint32_t)rq.y << 16), (int)(best & 0xFFu));
     int tx = (int)(cell & 0xFFFF), ty = (int)(cell >> 16);
     if (avail == 0) { tx = stg.x; ty = stg.y; }                                 // solvers.py:33-34
@@ -162,8 +160,6 @@ __global__ void __launch_bounds__(BLOCK) k_greedy(const __grid_constant__ KParam
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
-
 struct Shape { int G, RC; };
 
 static int fill_params(const wh_config *cfg, KParams &K, Shape &sh) {
@@ -182,14 +178,15 @@ static int fill_params(const wh_config *cfg, KParams &K, Shape &sh) {
         K.max_agents > K.R || K.wait > 32767 || K.wait < 1)
         return WH_E_CONFIG;
     for (int i = 0; i < K.L; ++i) if (K.racks[i] < 1 || K.racks[i] >= K.dim) return WH_E_CONFIG;
-    int G = next_pow2(K.R);
-    const int gp = next_pow2((K.P + 3) / 4);
-    if (gp > G) G = gp;
-    if (G < 4) G = 4;
+    int G = K.R;                         // one lane per agent / request ...
+    if ((K.P + 3) / 4 > G) G = (K.P + 3) / 4;   // ... and per 4 pickup points
+    if (G < 2) G = 2;
+    K.G = G;
+    K.invL = (256 + K.L - 1) / K.L;
     sh.G = G; sh.RC = 0;
-    if (K.R == 4 && G == 4) sh.RC = 4;
-    if (K.R == 9 && G == 16) sh.RC = 9;
-    if (K.R == 16 && G == 16) sh.RC = 16;
+    if (K.R == 4 && G == 4) sh.RC = 4;       // WarehouseSmall
+    if (K.R == 9 && G == 10) sh.RC = 9;      // WarehouseMedium: 3 envs per warp
+    if (K.R == 16 && G == 16) sh.RC = 16;    // WarehouseLarge
     return 0;
 }
 
@@ -211,30 +208,39 @@ static bool obs_ok(const wh_obs *o) {
 
 enum Kind { K_STEP, K_GSTEP, K_RESET, K_OBS, K_GREEDY };
 
-template <int G, int RC>
-static void launch_kind(Kind kind, const KParams &K, long long groups, cudaStream_t s) {
-    const long long threads = groups * G;
-    const unsigned grid = (unsigned)((threads + BLOCK - 1) / BLOCK);
+template <int GC, int RC>
+static void launch_kind(Kind kind, const KParams &K, cudaStream_t s) {
+    const int G = GC ? GC : K.G;
+    const long long epw = 32 / G, warps = (K.N + epw - 1) / epw;
+    const unsigned grid = (unsigned)((warps * 32 + BLOCK - 1) / BLOCK);
     switch (kind) {
-    case K_STEP: k_step<G, RC, false><<<grid, BLOCK, 0, s>>>(K); break;
-    case K_GSTEP: k_step<G, RC, true><<<grid, BLOCK, 0, s>>>(K); break;
-    case K_RESET: k_reset<G, RC><<<grid, BLOCK, 0, s>>>(K); break;
-    case K_OBS: k_obs<G, RC><<<grid, BLOCK, 0, s>>>(K); break;
-    case K_GREEDY: k_greedy<G, RC><<<grid, BLOCK, 0, s>>>(K); break;
+    case K_STEP: k_step<GC, RC, false><<<grid, BLOCK, 0, s>>>(K); break;
+    case K_GSTEP: k_step<GC, RC, true><<<grid, BLOCK, 0, s>>>(K); break;
+    case K_RESET: k_reset<GC, RC><<<grid, BLOCK, 0, s>>>(K); break;
+    case K_OBS: k_obs<GC, RC><<<grid, BLOCK, 0, s>>>(K); break;
+    default: break;
     }
+}
+
+template <int RC>
+static void launch_greedy(const KParams &K, cudaStream_t s) {
+    const long long rpw = 32 / K.R, warps = (K.N * K.R + rpw - 1) / rpw;   // agent rows per warp
+    const unsigned grid = (unsigned)((warps * 32 + BLOCK - 1) / BLOCK);
+    k_greedy<RC><<<grid, BLOCK, 0, s>>>(K);
 }
 
 static int launch(Kind kind, const KParams &K, const Shape &sh, void *stream) {
     if (K.N <= 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
-    const long long groups = (kind == K_GREEDY) ? K.N * K.R : K.N;
-    if (sh.RC == 4) launch_kind<4, 4>(kind, K, groups, s);
-    else if (sh.RC == 9) launch_kind<16, 9>(kind, K, groups, s);
-    else if (sh.RC == 16) launch_kind<16, 16>(kind, K, groups, s);
-    else if (sh.G == 4) launch_kind<4, 0>(kind, K, groups, s);
-    else if (sh.G == 8) launch_kind<8, 0>(kind, K, groups, s);
-    else if (sh.G == 16) launch_kind<16, 0>(kind, K, groups, s);
-    else launch_kind<32, 0>(kind, K, groups, s);
+    if (kind == K_GREEDY) {
+        if (sh.RC == 4) launch_greedy<4>(K, s);
+        else if (sh.RC == 9) launch_greedy<9>(K, s);
+        else if (sh.RC == 16) launch_greedy<16>(K, s);
+        else launch_greedy<0>(K, s);
+    } else if (sh.RC == 4) launch_kind<4, 4>(kind, K, s);
+    else if (sh.RC == 9) launch_kind<10, 9>(kind, K, s);
+    else if (sh.RC == 16) launch_kind<16, 16>(kind, K, s);
+    else launch_kind<0, 0>(kind, K, s);
     return (int)cudaGetLastError();
 }
 

@@ -1,14 +1,15 @@
 // wh_kernels.cuh — device code of the B200-native batched warehouse hot path (sm_100a).
 //
-// Mapping: one GROUP of G lanes (G = 4/8/16/32, a power-of-two slice of a warp) owns one
-// environment; 32/G environments share a warp and run in lock-step. Within a group
+// Mapping: one GROUP of G consecutive lanes (G = max(R, P/4): 4 for Small, 10 for Medium, 16 for
+// Large) owns one environment; floor(32/G) environments share a warp and run in lock-step (the
+// 32 mod G left-over lanes idle as "ghosts"). Within a group
 //   * lane a  (a < R) holds agent a: its cell (x | y<<8), its delivery target, its action;
 //   * lane l  holds pickup points 4l..4l+3: four int8 delivery targets packed in one 32-bit
 //     register and four timers;
 //   * lane r  (r < R) holds request r / "other agent" slot r while observations are written.
 // Everything that is per-env scalar (time, num_agents, the 64-bit active-request mask) is kept
-// redundantly in every lane of the group, so no shared memory round-trips are needed except one
-// 16-byte-per-request staging buffer used to compact the request list.
+// redundantly in every lane of the group; all exchange is by warp shuffles and ballots, no shared
+// memory is used.
 //
 // Reference semantics (file:line into ffahleraz/rllib-warehouse) are cited at each phase.
 #pragma once
@@ -31,6 +32,8 @@ constexpr uint32_t CTR_INIT_REQUESTS = 0xE0000000u;
 struct KParams {
     // geometry (core.py:92-108, variants.py)
     int R, dim, L, P, D, episode, wait, null_pos, max_agents, random_agents, regular_racks;
+    int G;      // lanes per environment
+    int invL;   // ceil(256 / L): q / L == (q * invL) >> 8 for q < 64, L <= 8
     int racks[WH_MAX_RACKS];
     // state (wh_state)
     int8_t *agent_pos, *agent_tgt, *pickup_tgt;
@@ -77,19 +80,25 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 
 __device__ __forceinline__ uint32_t bounded(uint32_t u, uint32_t n) { return __umulhi(u, n); }
 
-// index of the n-th (0-based, ascending) set bit of a 64-bit mask (n < popc(mask))
+// index of the n-th (0-based, ascending) set bit (n < popc(mask)); WIDE = mask may use bits >= 32
+template <bool WIDE>
 __device__ __forceinline__ int nth_set64(unsigned long long m, int n) {
     uint32_t w = (uint32_t)m;
-    int base = 0;
-    const int c = __popc(w);
-    if (n >= c) { n -= c; w = (uint32_t)(m >> 32); base = 32; }
     int pos = 0;
-#pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) {
-        const int cnt = __popc((w >> pos) & ((1u << s) - 1u));
-        if (n >= cnt) { n -= cnt; pos += s; }
+    if (WIDE) {
+        const int c = __popc(w);
+        if (n >= c) { n -= c; w = (uint32_t)(m >> 32); pos = 32; }
     }
-    return base + pos;
+    int c = __popc(w & 0xFFFFu);
+    if (n >= c) { n -= c; w >>= 16; pos += 16; }
+    c = __popc(w & 0xFFu);
+    if (n >= c) { n -= c; w >>= 8; pos += 8; }
+    c = __popc(w & 0xFu);
+    if (n >= c) { n -= c; w >>= 4; pos += 4; }
+    c = __popc(w & 0x3u);
+    if (n >= c) { n -= c; w >>= 2; pos += 2; }
+    if (n >= (int)(w & 1u)) pos += 1;
+    return pos;
 }
 
 // core.py:178-188  delivery point d -> cell, v = 2 + d/4, side = d%4: (v,0) (0,v) (v,dim-1) (dim-1,v)
@@ -104,7 +113,7 @@ __device__ __forceinline__ uint32_t delivery_cell16(int d, int dim) {
 // (-1,-1) (0,-1) (-1,0) (0,0)
 __device__ __forceinline__ uint32_t pickup_cell16(const KParams &P, int p) {
     const int q = p >> 2, c = p & 3;
-    const int rxi = q / P.L, ryi = q - rxi * P.L;
+    const int rxi = (q * P.invL) >> 8, ryi = q - rxi * P.L;
     const int rx = P.regular_racks ? 4 * (rxi + 1) : P.racks[rxi];
     const int ry = P.regular_racks ? 4 * (ryi + 1) : P.racks[ryi];
     return (uint32_t)(rx - 1 + (c & 1)) | ((uint32_t)(ry - 1 + (c >> 1)) << 8);
@@ -126,29 +135,92 @@ __device__ __forceinline__ int pickup_index(const KParams &P, int x, int y) {
     return (ix >= 0 && iy >= 0) ? 4 * (ix * P.L + iy) + ox + 2 * oy : -1;
 }
 
-template <int G>
+// A group of G consecutive lanes. GC = compile-time G (0 => runtime G from the launch parameters).
+template <int GC>
 struct Group {
-    int lane, gl;        // lane in warp, lane in group
-    uint32_t gmask;      // this group's lanes within the warp
-    int gshift;          // first lane of the group
-    __device__ __forceinline__ Group() {
+    int lane, gl;     // lane in warp, lane in group
+    int gshift;       // first lane of the group
+    int gi;           // group index inside the warp
+    int G, epw;       // lanes per group, groups (environments) per warp
+    uint32_t gmask;   // this group's lanes
+    bool ghost;       // one of the 32 mod G left-over lanes: computes along, owns nothing
+    static constexpr bool WIDE = (GC == 0) || (4 * GC > 32);   // pickup masks may need > 32 bits
+    static constexpr bool POW2 = GC != 0 && (GC & (GC - 1)) == 0;
+    __device__ __forceinline__ explicit Group(int g_runtime) {
+        G = GC ? GC : g_runtime;
+        epw = 32 / G;
         lane = threadIdx.x & 31;
-        gl = lane & (G - 1);
-        gshift = lane & ~(G - 1);
+        gi = lane / G;
+        ghost = gi >= epw;
+        gshift = ghost ? 0 : gi * G;
+        gl = ghost ? lane - epw * G : lane - gshift;
         gmask = (G == 32 ? FULL : ((1u << G) - 1u)) << gshift;
     }
     __device__ __forceinline__ uint32_t ballot(bool p) const {
         return (__ballot_sync(FULL, p) & gmask) >> gshift;
     }
-    __device__ __forceinline__ uint32_t shfl(uint32_t v, int src) const { return __shfl_sync(FULL, v, src, G); }
-    __device__ __forceinline__ uint32_t shfl_down1(uint32_t v) const { return __shfl_down_sync(FULL, v, 1, G); }
-    __device__ __forceinline__ unsigned long long or64(unsigned long long v) const {
-        const uint32_t lo = __reduce_or_sync(gmask, (uint32_t)v);
-        uint32_t hi = 0;
-        if (4 * G > 32) hi = __reduce_or_sync(gmask, (uint32_t)(v >> 32));
-        return (unsigned long long)lo | ((unsigned long long)hi << 32);
+    __device__ __forceinline__ uint32_t shfl(uint32_t v, int src) const {
+        return __shfl_sync(FULL, v, gshift + src);
     }
-    __device__ __forceinline__ int add(int v) const { return (int)__reduce_add_sync(gmask, (unsigned)v); }
+    __device__ __forceinline__ uint32_t shfl_down1(uint32_t v) const { return __shfl_down_sync(FULL, v, 1); }
+    // OR over the group of a per-lane nibble placed at bit 4*gl (natural pickup-index order)
+    __device__ __forceinline__ unsigned long long or_nibbles(uint32_t nib) const {
+        if (POW2) {
+            unsigned long long v = (gl < 16) ? ((unsigned long long)nib << (4 * gl)) : 0ull;
+            uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+#pragma unroll
+            for (int m = 1; m < (GC ? GC : 1); m <<= 1) {
+                lo |= __shfl_xor_sync(FULL, lo, m);
+                if (WIDE) hi |= __shfl_xor_sync(FULL, hi, m);
+            }
+            return (unsigned long long)lo | ((unsigned long long)hi << 32);
+        }
+        unsigned long long r = 0ull;
+        const int n = G < 16 ? G : 16;
+#pragma unroll
+        for (int s = 0; s < (GC ? (GC < 16 ? GC : 16) : 16); ++s)
+            if (s < n) r |= (unsigned long long)shfl(nib, s) << (4 * s);
+        return r;
+    }
+    __device__ __forceinline__ unsigned long long or64(unsigned long long v) const {
+        if (POW2) {
+            uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+#pragma unroll
+            for (int m = 1; m < (GC ? GC : 1); m <<= 1) {
+                lo |= __shfl_xor_sync(FULL, lo, m);
+                if (WIDE) hi |= __shfl_xor_sync(FULL, hi, m);
+            }
+            return (unsigned long long)lo | ((unsigned long long)hi << 32);
+        }
+        unsigned long long r = 0ull;
+        for (int s = 0; s < G; ++s) {
+            r |= (unsigned long long)shfl((uint32_t)v, s);
+            if (WIDE) r |= (unsigned long long)shfl((uint32_t)(v >> 32), s) << 32;
+        }
+        return r;
+    }
+    __device__ __forceinline__ uint32_t min_u32(uint32_t v) const {
+        if (POW2) {
+#pragma unroll
+            for (int m = 1; m < (GC ? GC : 1); m <<= 1) v = min(v, __shfl_xor_sync(FULL, v, m));
+            return v;
+        }
+        uint32_t r = 0xffffffffu;
+#pragma unroll
+        for (int s = 0; s < (GC ? GC : 32); ++s)
+            if (s < G) r = min(r, shfl(v, s));
+        return r;
+    }
+    __device__ __forceinline__ int add(int v) const {
+        if (POW2) {
+#pragma unroll
+            for (int m = 1; m < (GC ? GC : 1); m <<= 1) v += (int)__shfl_xor_sync(FULL, (uint32_t)v, m);
+            return v;
+        }
+        int r = 0;
+        for (int s = 0; s < G; ++s) r += (int)shfl((uint32_t)v, s);
+        return r;
+    }
 };
 
 // Registers of one lane of one environment.
@@ -160,8 +232,8 @@ struct EnvRegs {
     int time, A, ep;
 };
 
-template <int G>
-__device__ __forceinline__ void load_env(const KParams &P, const Group<G> &g, long long e, int R, EnvRegs &s) {
+template <int GC>
+__device__ __forceinline__ void load_env(const KParams &P, const Group<GC> &g, long long e, int R, EnvRegs &s) {
     s.time = P.time[e];
     s.A = P.num_agents[e];
     s.ep = P.episode_ctr[e];
@@ -181,8 +253,8 @@ __device__ __forceinline__ void load_env(const KParams &P, const Group<G> &g, lo
     }
 }
 
-template <int G>
-__device__ __forceinline__ void store_env(const KParams &P, const Group<G> &g, long long e, int R,
+template <int GC>
+__device__ __forceinline__ void store_env(const KParams &P, const Group<GC> &g, long long e, int R,
                                           const EnvRegs &s, bool store_meta) {
     if (g.gl < R) {
         reinterpret_cast<uint16_t *>(P.agent_pos)[e * R + g.gl] = (uint16_t)s.pos16;
@@ -202,13 +274,12 @@ __device__ __forceinline__ void store_env(const KParams &P, const Group<G> &g, l
 }
 
 // 64-bit mask of active requests in natural pickup-index order, replicated in every lane
-template <int G>
-__device__ __forceinline__ unsigned long long active_mask(const Group<G> &g, uint32_t pt4) {
-    uint32_t nib = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) nib |= (((pt4 >> (8 * j)) & 0xFFu) != 0xFFu) ? (1u << j) : 0u;
-    const unsigned long long v = (g.gl < 16) ? ((unsigned long long)nib << (4 * g.gl)) : 0ull;
-    return g.or64(v);
+template <int GC>
+__device__ __forceinline__ unsigned long long active_mask(const Group<GC> &g, uint32_t pt4) {
+    // byte != 0xFF  <=>  delivery index in 0..63  <=>  bit 7 clear
+    const uint32_t inv = ~pt4;
+    const uint32_t nib = ((inv >> 7) & 1u) | ((inv >> 14) & 2u) | ((inv >> 21) & 4u) | ((inv >> 28) & 8u);
+    return g.or_nibbles(nib);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -219,11 +290,11 @@ __device__ __forceinline__ unsigned long long active_mask(const Group<G> &g, uin
 //            occ[c] is True  <=>  some lane has mark == c.  A successful move from p clears the
 //            mark of EVERY agent standing on p (core.py:290 clears the bit even if a co-located
 //            agent remains) and sets the mover's mark to its new cell (core.py:291).
-//   rev/ca/cb : the up-to-three moves this agent's successful move forbids (core.py:294-297):
-//            the reverse move, and for a diagonal the two crossing moves.
+//   f0/f1/f2 : the up-to-three moves this agent's successful move forbids (core.py:294-297): the
+//            reverse move and, for a diagonal, the two crossing moves; armed once it has moved.
 // One ballot per processed agent answers "is the target marked, or is this move forbidden?".
-template <int G, int RC>
-__device__ __forceinline__ void do_moves(const KParams &P, const Group<G> &g, int R, int A,
+template <int GC, int RC>
+__device__ __forceinline__ void do_moves(const KParams &P, const Group<GC> &g, int R, int A,
                                          int act, int ord, bool have_order, uint32_t &pos16) {
     const int px = pos16 & 0xFF, py = pos16 >> 8;
     uint32_t m = ABSENT_MOVE, rev = ABSENT_MOVE, ca = ABSENT_MOVE, cb = ABSENT_MOVE;
@@ -243,7 +314,9 @@ __device__ __forceinline__ void do_moves(const KParams &P, const Group<G> &g, in
         }
     }
     uint32_t mark = (g.gl < A) ? pos16 : NO_CELL;   // core.py:276: every agent marks its cell
-    bool moved = false;
+    // armed forbidden moves; 0xFFFF0000-style values can never equal a real move (from-cell 0xFFFF
+    // never moves), and an ABSENT move is rejected below whatever `hit` says
+    uint32_t f0 = 0xFFFFFFFEu, f1 = 0xFFFFFFFEu, f2 = 0xFFFFFFFEu;
     int n_order = R;
     if (have_order) {  // entries after the first -1 are ignored
         const uint32_t neg = g.ballot(g.gl < R && ord < 0);
@@ -259,12 +332,12 @@ __device__ __forceinline__ void do_moves(const KParams &P, const Group<G> &g, in
         }
         uint32_t mm = g.shfl(m, cur < 0 ? 0 : cur);
         if (cur < 0) mm = ABSENT_MOVE;
-        const uint32_t c = mm >> 16;
-        const bool hit = (mark == c) || (moved && (rev == mm || ca == mm || cb == mm));
+        const uint32_t c = mm >> 16, from = mm & 0xFFFFu;
+        const bool hit = (mark == c) | (f0 == mm) | (f1 == mm) | (f2 == mm);
         const bool ok = (g.ballot(hit) == 0u) && (mm != ABSENT_MOVE);          // core.py:289
-        if (ok) {
-            if (mark == (mm & 0xFFFFu)) mark = NO_CELL;                        // core.py:290
-            if (g.gl == cur) { mark = c; pos16 = c; moved = true; }            // core.py:291,299-300
+        if (ok && mark == from) mark = NO_CELL;                                // core.py:290
+        if (ok && g.gl == cur) {                                               // core.py:291-300
+            mark = c; pos16 = c; f0 = rev; f1 = ca; f2 = cb;
         }
     }
 }
@@ -275,87 +348,94 @@ __device__ __forceinline__ void do_moves(const KParams &P, const Group<G> &g, in
 struct StepOut {
     float reward;
     unsigned long long active;  // active-request mask after respawn
+    uint32_t tpos16;            // delivery-target cell for the observation (null cell if none)
+    int npick, ndeliv, nexp;    // per-env event counts of this step
 };
 
-template <int G>
-__device__ __forceinline__ StepOut do_world(const KParams &P, const Group<G> &g, long long e, int R,
-                                            uint32_t env_id, EnvRegs &s, bool replay, int acc_out[3]) {
+template <int GC>
+__device__ __forceinline__ StepOut do_world(const KParams &P, const Group<GC> &g, long long e, int R,
+                                            uint32_t env_id, EnvRegs &s, bool replay) {
+    constexpr bool WIDE = Group<GC>::WIDE;
+    StepOut o;
     // ---- core.py:303-306 expiry (before pickup detection) ----
     int nexp = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const bool act = ((s.pt4 >> (8 * j)) & 0xFFu) != 0xFFu;
+        const bool act = ((s.pt4 >> (8 * j + 7)) & 1u) == 0u;
         s.tm[j] -= act ? 1 : 0;
         if (s.tm[j] == 0) { s.pt4 |= 0xFFu << (8 * j); s.tm[j] = -1; ++nexp; }
     }
+    o.nexp = __any_sync(FULL, nexp != 0) ? g.add(nexp) : 0;
     // ---- core.py:309-335 pickups: agent on a pickup cell, free, request waiting there ----
     const int x = s.pos16 & 0xFF, y = s.pos16 >> 8;
     const int cand = (g.gl < s.A) ? pickup_index(P, x, y) : -1;
     const uint32_t w = g.shfl(s.pt4, (cand < 0 ? 0 : cand) >> 2);
     const int tg = (int)(int8_t)((w >> (8 * (cand & 3))) & 0xFFu);
     const bool picks = cand >= 0 && s.atgt == -1 && tg > -1;
-    const unsigned long long served = g.or64(picks ? (1ull << cand) : 0ull);
-    {
+    float reward = 0.0f;
+    o.npick = 0;
+    if (__any_sync(FULL, picks)) {                  // rare: most env-steps see no pickup
+        const unsigned long long served = g.or64(picks ? (1ull << cand) : 0ull);
         const uint32_t nib = (g.gl < 16) ? (uint32_t)((served >> (4 * g.gl)) & 0xFull) : 0u;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
             if ((nib >> j) & 1u) { s.pt4 |= 0xFFu << (8 * j); s.tm[j] = -1; }  // core.py:330-331
+        if (picks) { s.atgt = tg; reward = 1.0f; }                             // core.py:327-329,335
+        o.npick = __popc(g.ballot(picks));
     }
-    float reward = 0.0f;
-    if (picks) { s.atgt = tg; reward = 1.0f; }                                 // core.py:327-329,335
-    const int npick = __popc(g.ballot(picks));
-
     // ---- core.py:338-351 respawn until exactly R requests are active ----
     unsigned long long active = active_mask(g, s.pt4);
-    const unsigned long long pmask = (P.P >= 64) ? ~0ull : ((1ull << P.P) - 1ull);
     int sp = -1, st_ = -1, k;
     uint32_t up = 0, ut = 0;
     if (replay) {
         if (g.gl < R) { sp = P.spawn_p[e * R + g.gl]; st_ = P.spawn_t[e * R + g.gl]; }
-        const uint32_t neg = g.ballot(sp < 0);       // lanes >= R hold -1, so neg != 0 unless G == R
-        k = neg ? (__ffs(neg) - 1) : G;
+        const uint32_t neg = g.ballot(sp < 0);       // lanes >= R hold -1
+        k = neg ? (__ffs(neg) - 1) : g.G;
     } else {
         k = R - __popcll(active);
         if (k < 0) k = 0;
-        if (__any_sync(FULL, k > 0))
-            philox4x32_10(env_id, (uint32_t)s.ep, (uint32_t)s.time, (uint32_t)g.gl, P.seed, up, ut);
     }
-    unsigned long long inactive = ~active & pmask;
-    unsigned long long avail_d = (P.D >= 64) ? ~0ull : ((1ull << P.D) - 1ull);
-    int n_inact = __popcll(inactive);
-    for (int i = 0; __any_sync(FULL, i < k); ++i) {
-        int p, d;
-        if (replay) {
-            p = (int)g.shfl((uint32_t)sp, i);
-            d = (int)g.shfl((uint32_t)st_, i);
-        } else {
-            const uint32_t a = g.shfl(up, i), b = g.shfl(ut, i);
-            const int ni = n_inact - i, di = P.D - i;
-            p = nth_set64(inactive, (int)bounded(a, (uint32_t)(ni > 0 ? ni : 1)));
-            d = nth_set64(avail_d, (int)bounded(b, (uint32_t)(di > 0 ? di : 1)));
-        }
-        if (i < k && p >= 0) {
-            inactive &= ~(1ull << p);
-            avail_d &= ~(1ull << d);
-            active |= 1ull << p;
-            if ((p >> 2) == g.gl) {                                           // core.py:344,351
-                const int j = p & 3;
-                s.pt4 = (s.pt4 & ~(0xFFu << (8 * j))) | (((uint32_t)d & 0xFFu) << (8 * j));
+    if (__any_sync(FULL, k > 0)) {
+        if (!replay) philox4x32_10(env_id, (uint32_t)s.ep, (uint32_t)s.time, (uint32_t)g.gl, P.seed, up, ut);
+        const unsigned long long pmask = (P.P >= 64) ? ~0ull : ((1ull << P.P) - 1ull);
+        unsigned long long inactive = ~active & pmask;
+        unsigned long long avail_d = (P.D >= 64) ? ~0ull : ((1ull << P.D) - 1ull);
+        const int n_inact = __popcll(inactive);
+        for (int i = 0; __any_sync(FULL, i < k); ++i) {
+            int p, d;
+            if (replay) {
+                p = (int)g.shfl((uint32_t)sp, i);
+                d = (int)g.shfl((uint32_t)st_, i);
+            } else {
+                const uint32_t a = g.shfl(up, i), b = g.shfl(ut, i);
+                const int ni = n_inact - i, di = P.D - i;
+                p = nth_set64<WIDE>(inactive, (int)bounded(a, (uint32_t)(ni > 0 ? ni : 1)));
+                d = nth_set64<true>(avail_d, (int)bounded(b, (uint32_t)(di > 0 ? di : 1)));
+            }
+            if (i < k && p >= 0) {
+                inactive &= ~(1ull << p);
+                avail_d &= ~(1ull << d);
+                active |= 1ull << p;
+                if ((p >> 2) == g.gl) {                                       // core.py:344,351
+                    const int j = p & 3;
+                    s.pt4 = (s.pt4 & ~(0xFFu << (8 * j))) | (((uint32_t)d & 0xFFu) << (8 * j));
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) if (jj == j) s.tm[jj] = P.wait;
+                    for (int jj = 0; jj < 4; ++jj) if (jj == j) s.tm[jj] = P.wait;
+                }
             }
         }
     }
     // ---- core.py:354-368 deliveries (an agent that picked up THIS step is already delivering) ----
+    const uint32_t null16 = (uint32_t)P.null_pos | ((uint32_t)P.null_pos << 8);
+    o.tpos16 = null16;
     bool delivered = false;
     if (g.gl < s.A && s.atgt > -1) {
-        delivered = delivery_cell16(s.atgt, P.dim) == s.pos16;
+        const uint32_t dcell = delivery_cell16(s.atgt, P.dim);
+        delivered = dcell == s.pos16;
         if (delivered) { s.atgt = -1; reward += 1.0f; }
+        else o.tpos16 = dcell;
     }
-    acc_out[0] = npick;
-    acc_out[1] = __popc(g.ballot(delivered));
-    acc_out[2] = g.add(nexp);
-    StepOut o;
+    o.ndeliv = __any_sync(FULL, delivered) ? __popc(g.ballot(delivered)) : 0;
     o.reward = reward;
     o.active = active;
     return o;
@@ -365,14 +445,16 @@ __device__ __forceinline__ StepOut do_world(const KParams &P, const Group<G> &g,
 // S9  observation build — core.py:371-432 (step flavour), core.py:224-260 (reset flavour)
 // ---------------------------------------------------------------------------------------------
 // Lane r holds padded row r of the three per-agent tables (position, availability, delivery-target
-// position) plus row r+1 (one shuffle), so "table with row a deleted" is a per-lane select. Every
-// store instruction writes one contiguous run per environment: 16R bytes (requests, 128-bit
-// stores), 8(R-1) bytes (other_*), consecutive agents a are adjacent, so each key's [R, ...] block
-// of an environment is written as one dense stream.
-template <int G, int RC>
-__device__ __forceinline__ void build_obs(const KParams &P, const Group<G> &g, long long e, int R,
-                                          const EnvRegs &s, unsigned long long active, int flavour,
-                                          int4 *sreq /* [R] staging for this group */, bool live) {
+// position) plus row r+1 (one shuffle), so "table with row a deleted" is a per-lane select; lane r
+// also materialises request r (r-th set bit of the active mask -> pickup cell, delivery cell).
+// Every store instruction writes one contiguous run per environment: 16R bytes (requests, 128-bit
+// stores), 8(R-1) bytes (other_*); consecutive agents a are adjacent, so each key's [R, ...] block
+// of an environment is written as one dense stream (st.global.cs, written once, never re-read here).
+template <int GC, int RC>
+__device__ __forceinline__ void build_obs(const KParams &P, const Group<GC> &g, long long e, int R,
+                                          const EnvRegs &s, unsigned long long active, uint32_t tpos16,
+                                          int flavour, bool live) {
+    constexpr bool WIDE = Group<GC>::WIDE;
     const int null_pos = P.null_pos;
     const uint32_t null16 = (uint32_t)null_pos | ((uint32_t)null_pos << 8);
     const bool real = g.gl < s.A;
@@ -380,7 +462,7 @@ __device__ __forceinline__ void build_obs(const KParams &P, const Group<G> &g, l
     // core.py:372-407 padded tables (reset flavour: availability 0 and null targets, core.py:233-236)
     const uint32_t ppos = real ? s.pos16 : null16;
     const uint32_t avail = (flavour == WH_OBS_STEP && real && !delivering) ? 1u : 0u;
-    const uint32_t tpos = (flavour == WH_OBS_STEP && delivering) ? delivery_cell16(s.atgt, P.dim) : null16;
+    const uint32_t tpos = (flavour == WH_OBS_STEP && delivering) ? tpos16 : null16;
     const uint32_t mine = (ppos & 0x7Fu) | (((ppos >> 8) & 0x7Fu) << 7) | ((tpos & 0x7Fu) << 14) |
                           (((tpos >> 8) & 0x7Fu) << 21) | (avail << 28);
     const uint32_t next = g.shfl_down1(mine);
@@ -390,22 +472,15 @@ __device__ __forceinline__ void build_obs(const KParams &P, const Group<G> &g, l
     const int my_a = (mine >> 28) & 1, nx_a = (next >> 28) & 1;
 
     // core.py:409-418 request list: active pickup points in ascending index, [px,py,dx,dy]
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int p = 4 * g.gl + j;
-        const uint32_t b = (s.pt4 >> (8 * j)) & 0xFFu;
-        if (b != 0xFFu && p < 64) {
-            const int rank = __popcll(active & ((1ull << p) - 1ull));
-            if (rank < R) {
-                const uint32_t pc = pickup_cell16(P, p), dc = delivery_cell16((int)b, P.dim);
-                sreq[rank] = make_int4(pc & 0xFF, pc >> 8, dc & 0xFF, dc >> 8);
-            }
-        }
-    }
-    __syncwarp();
+    const bool have = g.gl < R && g.gl < __popcll(active);
+    const int p = nth_set64<WIDE>(active, have ? g.gl : 0) & 63;
+    const uint32_t w4 = g.shfl(s.pt4, p >> 2);
     int4 rq = make_int4(null_pos, null_pos, null_pos, null_pos);  // only if < R active (unreachable)
-    if (g.gl < R && g.gl < __popcll(active)) rq = sreq[g.gl];
-    __syncwarp();
+    if (have) {
+        const uint32_t pc = pickup_cell16(P, p);
+        const uint32_t dc = delivery_cell16((int)((w4 >> (8 * (p & 3))) & 0x3Fu), P.dim);
+        rq = make_int4(pc & 0xFF, pc >> 8, dc & 0xFF, dc >> 8);
+    }
     if (!live) return;
 
     const wh_obs &o = P.obs;
@@ -435,18 +510,24 @@ __device__ __forceinline__ void build_obs(const KParams &P, const Group<G> &g, l
     }
 }
 
+// delivery-target cell of my agent for the observation tables (null cell when not delivering)
+__device__ __forceinline__ uint32_t target_cell16(const KParams &P, int atgt) {
+    return atgt > -1 ? delivery_cell16(atgt, P.dim) : ((uint32_t)P.null_pos | ((uint32_t)P.null_pos << 8));
+}
+
 // ---------------------------------------------------------------------------------------------
 // reset — core.py:167-221, variants.py:69-74
 // ---------------------------------------------------------------------------------------------
-template <int G>
-__device__ __forceinline__ unsigned long long do_reset(const KParams &P, const Group<G> &g, long long e,
+template <int GC>
+__device__ __forceinline__ unsigned long long do_reset(const KParams &P, const Group<GC> &g, long long e,
                                                        int R, uint32_t env_id, EnvRegs &s, bool replay,
                                                        bool doit) {
+    constexpr bool WIDE = Group<GC>::WIDE;
     // `doit` is uniform within the group; groups that skip still take part in warp-wide votes
     EnvRegs n = s;
     n.ep = s.ep + 1;
     n.time = 0;                                                                // core.py:168
-    uint32_t u0, u1;
+    uint32_t u0 = 0, u1 = 0;
     if (replay) {
         if (P.r_num_agents) n.A = P.r_num_agents[e];
     } else if (P.random_agents) {                                             // variants.py:70,74
@@ -489,8 +570,8 @@ __device__ __forceinline__ unsigned long long do_reset(const KParams &P, const G
             d = (int)g.shfl((uint32_t)st_, i);
         } else {
             const uint32_t a = g.shfl(u0, i), b = g.shfl(u1, i);
-            p = nth_set64(inactive, (int)bounded(a, (uint32_t)(P.P - i)));
-            d = nth_set64(avail_d, (int)bounded(b, (uint32_t)(P.D - i)));
+            p = nth_set64<WIDE>(inactive, (int)bounded(a, (uint32_t)(P.P - i)));
+            d = nth_set64<true>(avail_d, (int)bounded(b, (uint32_t)(P.D - i)));
         }
         if (p >= 0) {
             inactive &= ~(1ull << p);
@@ -516,18 +597,21 @@ __device__ __forceinline__ unsigned long long do_reset(const KParams &P, const G
 // (core.py:233-236), so agents head for the map centre; otherwise a free agent goes to the
 // L1-nearest request (first minimum in request order == ascending pickup index), a delivering
 // agent to its delivery cell.
-template <int G>
-__device__ __forceinline__ int greedy_from_state(const KParams &P, const Group<G> &g, int R,
+template <int GC, int RC>
+__device__ __forceinline__ int greedy_from_state(const KParams &P, const Group<GC> &g, int R,
                                                  uint32_t env_id, const EnvRegs &s) {
+    constexpr bool WIDE = Group<GC>::WIDE;
     const unsigned long long active = active_mask(g, s.pt4);
     const int px = s.pos16 & 0xFF, py = s.pos16 >> 8;
     // lane r takes the r-th active pickup point's cell
     const int nact = __popcll(active);
     uint32_t cell = (uint32_t)P.null_pos | ((uint32_t)P.null_pos << 8);
-    if (g.gl < nact && g.gl < R) cell = pickup_cell16(P, nth_set64(active, g.gl));
+    if (g.gl < nact && g.gl < R) cell = pickup_cell16(P, nth_set64<WIDE>(active, g.gl));
     int best = 1 << 30;
     uint32_t bcell = 0;
-    for (int r = 0; r < R; ++r) {                                              // solvers.py:53-58
+    const int RR = RC ? RC : R;
+#pragma unroll
+    for (int r = 0; r < RR; ++r) {                                             // solvers.py:53-58
         const uint32_t c = g.shfl(cell, r);
         const int d = abs(px - (int)(c & 0xFF)) + abs(py - (int)(c >> 8));
         if (d < best) { best = d; bcell = c; }
