@@ -27,10 +27,23 @@ struct Tile {
     }
 };
 
+// per-block staging for the observation build: one ObsStage per environment slot of the block
+template <int GC, int RC>
+struct StageMem {
+    static constexpr int EPW = GC ? 32 / GC : 1;
+    static constexpr int BYTES = RC ? (BLOCK / 32) * EPW * ObsStage<RC>::BYTES : 16;
+    __device__ static __forceinline__ unsigned char *mine(unsigned char *base, const Group<GC> &g) {
+        if (RC == 0) return nullptr;
+        const int slot = (threadIdx.x >> 5) * EPW + (g.ghost ? 0 : g.gi);
+        return base + slot * ObsStage<RC>::BYTES;
+    }
+};
+
 // Warehouse.step (+ optional in-kernel greedy solver, + optional observation build, + optional
 // auto-reset) — core.py:262-442, solvers.py:27-58
 template <int GC, int RC, bool GREEDY>
 __global__ void __launch_bounds__(BLOCK) k_step(const __grid_constant__ KParams P) {
+    __shared__ __align__(16) unsigned char smem[StageMem<GC, RC>::BYTES];
     const Group<GC> g(P.G);
     const Tile<GC> t(P, g);
     const int R = RC ? RC : P.R;
@@ -84,12 +97,13 @@ __global__ void __launch_bounds__(BLOCK) k_step(const __grid_constant__ KParams 
         meta = true;
     }
     if (t.live) store_env(P, g, e, R, s, meta);
-    if (P.obs.requests) build_obs<GC, RC>(P, g, e, R, s, active, tpos16, flavour, t.live);
+    if (P.obs.requests) build_obs<GC, RC>(P, g, e, R, s, active, tpos16, flavour, t.live, StageMem<GC, RC>::mine(smem, g));
 }
 
 // Warehouse.reset — core.py:167-260
 template <int GC, int RC>
 __global__ void __launch_bounds__(BLOCK) k_reset(const __grid_constant__ KParams P) {
+    __shared__ __align__(16) unsigned char smem[StageMem<GC, RC>::BYTES];
     const Group<GC> g(P.G);
     const Tile<GC> t(P, g);
     const int R = RC ? RC : P.R;
@@ -103,19 +117,20 @@ __global__ void __launch_bounds__(BLOCK) k_reset(const __grid_constant__ KParams
         store_env(P, g, e, R, s, true);
         if (g.gl == 0) reinterpret_cast<int4 *>(P.acc)[e] = make_int4(0, 0, 0, 0);
     }
-    if (P.obs.requests) build_obs<GC, RC>(P, g, e, R, s, active, 0u, WH_OBS_RESET, doit);
+    if (P.obs.requests) build_obs<GC, RC>(P, g, e, R, s, active, 0u, WH_OBS_RESET, doit, StageMem<GC, RC>::mine(smem, g));
 }
 
 // observation build alone — core.py:224-260 / 371-432
 template <int GC, int RC>
 __global__ void __launch_bounds__(BLOCK) k_obs(const __grid_constant__ KParams P) {
+    __shared__ __align__(16) unsigned char smem[StageMem<GC, RC>::BYTES];
     const Group<GC> g(P.G);
     const Tile<GC> t(P, g);
     const int R = RC ? RC : P.R;
     EnvRegs s;
     load_env(P, g, t.e, R, s);
     const unsigned long long active = active_mask(g, s.pt4);
-    build_obs<GC, RC>(P, g, t.e, R, s, active, target_cell16(P, s.atgt), P.flavour, t.live);
+    build_obs<GC, RC>(P, g, t.e, R, s, active, target_cell16(P, s.atgt), P.flavour, t.live, StageMem<GC, RC>::mine(smem, g));
 }
 
 // WarehouseRandomGreedySolver.compute_action on observation tensors — solvers.py:27-58.

@@ -8,8 +8,8 @@
 //     register and four timers;
 //   * lane r  (r < R) holds request r / "other agent" slot r while observations are written.
 // Everything that is per-env scalar (time, num_agents, the 64-bit active-request mask) is kept
-// redundantly in every lane of the group; all exchange is by warp shuffles and ballots, no shared
-// memory is used.
+// redundantly in every lane of the group; all exchange is by warp shuffles and ballots. Shared
+// memory is used only to stage the small-row observation keys for full-width stores.
 //
 // Reference semantics (file:line into ffahleraz/rllib-warehouse) are cited at each phase.
 #pragma once
@@ -447,13 +447,22 @@ __device__ __forceinline__ StepOut do_world(const KParams &P, const Group<GC> &g
 // Lane r holds padded row r of the three per-agent tables (position, availability, delivery-target
 // position) plus row r+1 (one shuffle), so "table with row a deleted" is a per-lane select; lane r
 // also materialises request r (r-th set bit of the active mask -> pickup cell, delivery cell).
-// Every store instruction writes one contiguous run per environment: 16R bytes (requests, 128-bit
-// stores), 8(R-1) bytes (other_*); consecutive agents a are adjacent, so each key's [R, ...] block
-// of an environment is written as one dense stream (st.global.cs, written once, never re-read here).
+// requests: every 128-bit store instruction writes 16R contiguous bytes per environment straight from
+// registers. other_*: one environment's block of a key is assembled in shared memory and streamed
+// out with 128-bit stores (st.global.cs: written once, never re-read here).
+// Shared-memory staging area of one environment while its observation is written (compile-time R).
+template <int RC>
+struct ObsStage {
+    static constexpr int ROWS = RC * (RC - 1);          // "other" rows of one env
+    static constexpr int POS_BYTES = 8 * ROWS;          // other_positions / other_delivery_targets
+    static constexpr int AV_BYTES = ROWS;               // other_availabilities
+    static constexpr int BYTES = RC ? ((POS_BYTES + AV_BYTES + 15) / 16) * 16 : 16;
+};
+
 template <int GC, int RC>
 __device__ __forceinline__ void build_obs(const KParams &P, const Group<GC> &g, long long e, int R,
                                           const EnvRegs &s, unsigned long long active, uint32_t tpos16,
-                                          int flavour, bool live) {
+                                          int flavour, bool live, unsigned char *stage) {
     constexpr bool WIDE = Group<GC>::WIDE;
     const int null_pos = P.null_pos;
     const uint32_t null16 = (uint32_t)null_pos | ((uint32_t)null_pos << 8);
@@ -481,24 +490,71 @@ __device__ __forceinline__ void build_obs(const KParams &P, const Group<GC> &g, 
         const uint32_t dc = delivery_cell16((int)((w4 >> (8 * (p & 3))) & 0x3Fu), P.dim);
         rq = make_int4(pc & 0xFF, pc >> 8, dc & 0xFF, dc >> 8);
     }
-    if (!live) return;
 
     const wh_obs &o = P.obs;
     const long long row0 = e * R;
-    if (g.gl < R) {
+    if (live && g.gl < R) {
         o.num_agents[row0 + g.gl] = s.A;
         reinterpret_cast<int2 *>(o.self_position)[row0 + g.gl] = my_p;
         o.self_availability[row0 + g.gl] = (int8_t)my_a;
         reinterpret_cast<int2 *>(o.self_delivery_target)[row0 + g.gl] = my_t;
     }
-    int2 *op = reinterpret_cast<int2 *>(o.other_positions) + row0 * (R - 1) + g.gl;
-    int2 *ot = reinterpret_cast<int2 *>(o.other_delivery_targets) + row0 * (R - 1) + g.gl;
-    int8_t *oa = o.other_availabilities + row0 * (R - 1) + g.gl;
     int4 *orq = reinterpret_cast<int4 *>(o.requests) + row0 * R + g.gl;
     // core.py:428 quirk: in step() other_delivery_targets always drops row 1 (reset drops row i)
     const int2 t_fixed = (g.gl >= 1) ? nx_t : my_t;
     const int RR = RC ? RC : R;
+
+    if constexpr (RC != 0) {
+        // The "other_*" keys have 8-byte / 1-byte rows: written straight from registers they would
+        // leave partially filled 32-byte sectors on the SM->L2 path. Stage one environment's
+        // [R, R-1, ...] block in shared memory and stream it out with 128-bit / 32-bit stores.
+        using St = ObsStage<RC>;
+        int2 *s_pos = reinterpret_cast<int2 *>(stage);
+        int8_t *s_av = reinterpret_cast<int8_t *>(stage + St::POS_BYTES);
+        int4 *d_pos = reinterpret_cast<int4 *>(o.other_positions) + row0 * (RC - 1) / 2;
+        int4 *d_tgt = reinterpret_cast<int4 *>(o.other_delivery_targets) + row0 * (RC - 1) / 2;
+        int32_t *d_av = reinterpret_cast<int32_t *>(o.other_availabilities + row0 * (RC - 1));
 #pragma unroll
+        for (int a = 0; a < RC; ++a) {
+            if (live && g.gl < RC) __stcs(orq + a * RC, rq);                    // core.py:429
+            if (g.gl < RC - 1) {
+                const bool sh = g.gl >= a;                                      // core.py:426-427
+                s_pos[a * (RC - 1) + g.gl] = sh ? nx_p : my_p;
+                s_av[a * (RC - 1) + g.gl] = (int8_t)(sh ? nx_a : my_a);
+            }
+        }
+        __syncwarp();
+        if (live) {
+#pragma unroll
+            for (int k = 0; k < (St::ROWS / 2 + GC - 1) / GC; ++k) {
+                const int i = g.gl + k * GC;
+                if (i < St::ROWS / 2) __stcs(d_pos + i, reinterpret_cast<const int4 *>(stage)[i]);
+            }
+#pragma unroll
+            for (int k = 0; k < (St::ROWS / 4 + GC - 1) / GC; ++k) {
+                const int i = g.gl + k * GC;
+                if (i < St::ROWS / 4) __stcs(d_av + i, reinterpret_cast<const int32_t *>(s_av)[i]);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int a = 0; a < RC; ++a)
+            if (g.gl < RC - 1)
+                s_pos[a * (RC - 1) + g.gl] = flavour == WH_OBS_STEP ? t_fixed : ((g.gl >= a) ? nx_t : my_t);
+        __syncwarp();
+        if (live) {
+#pragma unroll
+            for (int k = 0; k < (St::ROWS / 2 + GC - 1) / GC; ++k) {
+                const int i = g.gl + k * GC;
+                if (i < St::ROWS / 2) __stcs(d_tgt + i, reinterpret_cast<const int4 *>(stage)[i]);
+            }
+        }
+        return;
+    }
+    if (!live) return;
+    int2 *op = reinterpret_cast<int2 *>(o.other_positions) + row0 * (R - 1) + g.gl;
+    int2 *ot = reinterpret_cast<int2 *>(o.other_delivery_targets) + row0 * (R - 1) + g.gl;
+    int8_t *oa = o.other_availabilities + row0 * (R - 1) + g.gl;
     for (int a = 0; a < RR; ++a) {
         if (g.gl < R - 1) {
             const bool sh = g.gl >= a;                                          // core.py:426-427
