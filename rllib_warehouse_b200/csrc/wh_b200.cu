@@ -42,7 +42,7 @@ struct StageMem {
 // Warehouse.step (+ optional in-kernel greedy solver, + optional observation build, + optional
 // auto-reset) — core.py:262-442, solvers.py:27-58
 template <int GC, int RC, bool GREEDY>
-__global__ void __launch_bounds__(BLOCK) k_step(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(BLOCK, 5) k_step(const __grid_constant__ KParams P) {
     __shared__ __align__(16) unsigned char smem[StageMem<GC, RC>::BYTES];
     const Group<GC> g(P.G);
     const Tile<GC> t(P, g);
@@ -200,7 +200,7 @@ static int fill_params(const wh_config *cfg, KParams &K, Shape &sh) {
     K.invL = (256 + K.L - 1) / K.L;
     sh.G = G; sh.RC = 0;
     if (K.R == 4 && G == 4) sh.RC = 4;       // WarehouseSmall
-    if (K.R == 9 && G == 10) sh.RC = 9;      // WarehouseMedium: 3 envs per warp
+    if (K.R == 9 && G == 9) sh.RC = 9;       // WarehouseMedium: 3 envs per warp
     if (K.R == 16 && G == 16) sh.RC = 16;    // WarehouseLarge
     return 0;
 }
@@ -253,7 +253,7 @@ static int launch(Kind kind, const KParams &K, const Shape &sh, void *stream) {
         else if (sh.RC == 16) launch_greedy<16>(K, s);
         else launch_greedy<0>(K, s);
     } else if (sh.RC == 4) launch_kind<4, 4>(kind, K, s);
-    else if (sh.RC == 9) launch_kind<10, 9>(kind, K, s);
+    else if (sh.RC == 9) launch_kind<9, 9>(kind, K, s);
     else if (sh.RC == 16) launch_kind<16, 16>(kind, K, s);
     else launch_kind<0, 0>(kind, K, s);
     return (int)cudaGetLastError();

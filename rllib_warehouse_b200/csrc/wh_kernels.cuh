@@ -1,6 +1,6 @@
 // wh_kernels.cuh — device code of the B200-native batched warehouse hot path (sm_100a).
 //
-// Mapping: one GROUP of G consecutive lanes (G = max(R, P/4): 4 for Small, 10 for Medium, 16 for
+// Mapping: one GROUP of G consecutive lanes (G = max(R, P/4): 4 for Small, 9 for Medium, 16 for
 // Large) owns one environment; floor(32/G) environments share a warp and run in lock-step (the
 // 32 mod G left-over lanes idle as "ghosts"). Within a group
 //   * lane a  (a < R) holds agent a: its cell (x | y<<8), its delivery target, its action;
@@ -323,21 +323,28 @@ __device__ __forceinline__ void do_moves(const KParams &P, const Group<GC> &g, i
         n_order = neg ? (__ffs(neg) - 1) : R;
     }
     const int RR = RC ? RC : R;
+    if (have_order) {
 #pragma unroll
-    for (int t = 0; t < RR; ++t) {
-        int cur = t;
-        if (have_order) {
-            cur = (int)g.shfl((uint32_t)ord, t);
+        for (int t = 0; t < RR; ++t) {
+            int cur = (int)g.shfl((uint32_t)ord, t);
             if (t >= n_order || cur >= R) cur = -1;
+            uint32_t mm = g.shfl(m, cur < 0 ? 0 : cur);
+            if (cur < 0) mm = ABSENT_MOVE;
+            const uint32_t c = mm >> 16, from = mm & 0xFFFFu;
+            const bool hit = (mark == c) | (f0 == mm) | (f1 == mm) | (f2 == mm);
+            const bool ok = (g.ballot(hit) == 0u) && (mm != ABSENT_MOVE);      // core.py:289
+            if (ok && mark == from) mark = NO_CELL;                            // core.py:290
+            if (ok && g.gl == cur) { mark = c; pos16 = c; f0 = rev; f1 = ca; f2 = cb; }   // core.py:291-300
         }
-        uint32_t mm = g.shfl(m, cur < 0 ? 0 : cur);
-        if (cur < 0) mm = ABSENT_MOVE;
-        const uint32_t c = mm >> 16, from = mm & 0xFFFFu;
-        const bool hit = (mark == c) | (f0 == mm) | (f1 == mm) | (f2 == mm);
-        const bool ok = (g.ballot(hit) == 0u) && (mm != ABSENT_MOVE);          // core.py:289
-        if (ok && mark == from) mark = NO_CELL;                                // core.py:290
-        if (ok && g.gl == cur) {                                               // core.py:291-300
-            mark = c; pos16 = c; f0 = rev; f1 = ca; f2 = cb;
+    } else {
+#pragma unroll
+        for (int t = 0; t < RR; ++t) {                                         // ascending agent ids
+            const uint32_t mm = g.shfl(m, t);
+            const uint32_t c = mm >> 16, from = mm & 0xFFFFu;
+            const bool hit = (mark == c) | (f0 == mm) | (f1 == mm) | (f2 == mm);
+            const bool ok = (g.ballot(hit) == 0u) && (mm != ABSENT_MOVE);      // core.py:289
+            if (ok && mark == from) mark = NO_CELL;                            // core.py:290
+            if (ok && g.gl == t) { mark = c; pos16 = c; f0 = rev; f1 = ca; f2 = cb; }     // core.py:291-300
         }
     }
 }
@@ -514,10 +521,11 @@ __device__ __forceinline__ void build_obs(const KParams &P, const Group<GC> &g, 
         int4 *d_pos = reinterpret_cast<int4 *>(o.other_positions) + row0 * (RC - 1) / 2;
         int4 *d_tgt = reinterpret_cast<int4 *>(o.other_delivery_targets) + row0 * (RC - 1) / 2;
         int32_t *d_av = reinterpret_cast<int32_t *>(o.other_availabilities + row0 * (RC - 1));
+        const bool writer = !g.ghost && g.gl < RC - 1;   // ghost lanes shadow group 0: keep them off its stage
 #pragma unroll
         for (int a = 0; a < RC; ++a) {
             if (live && g.gl < RC) __stcs(orq + a * RC, rq);                    // core.py:429
-            if (g.gl < RC - 1) {
+            if (writer) {
                 const bool sh = g.gl >= a;                                      // core.py:426-427
                 s_pos[a * (RC - 1) + g.gl] = sh ? nx_p : my_p;
                 s_av[a * (RC - 1) + g.gl] = (int8_t)(sh ? nx_a : my_a);
@@ -537,16 +545,29 @@ __device__ __forceinline__ void build_obs(const KParams &P, const Group<GC> &g, 
             }
         }
         __syncwarp();
+        if (flavour == WH_OBS_STEP) {
+            // every agent's other_delivery_targets block is the same (R-1)-row table (core.py:428):
+            // stage two copies (= R-1 whole int4) and stream them out R/2 times over
+            if (writer) { s_pos[g.gl] = t_fixed; s_pos[RC - 1 + g.gl] = t_fixed; }
+            __syncwarp();
+            if (live) {
 #pragma unroll
-        for (int a = 0; a < RC; ++a)
-            if (g.gl < RC - 1)
-                s_pos[a * (RC - 1) + g.gl] = flavour == WH_OBS_STEP ? t_fixed : ((g.gl >= a) ? nx_t : my_t);
-        __syncwarp();
-        if (live) {
+                for (int k = 0; k < (St::ROWS / 2 + GC - 1) / GC; ++k) {
+                    const int i = g.gl + k * GC;
+                    if (i < St::ROWS / 2) __stcs(d_tgt + i, reinterpret_cast<const int4 *>(stage)[i % (RC - 1)]);
+                }
+            }
+        } else {
 #pragma unroll
-            for (int k = 0; k < (St::ROWS / 2 + GC - 1) / GC; ++k) {
-                const int i = g.gl + k * GC;
-                if (i < St::ROWS / 2) __stcs(d_tgt + i, reinterpret_cast<const int4 *>(stage)[i]);
+            for (int a = 0; a < RC; ++a)
+                if (writer) s_pos[a * (RC - 1) + g.gl] = (g.gl >= a) ? nx_t : my_t;   // core.py:256
+            __syncwarp();
+            if (live) {
+#pragma unroll
+                for (int k = 0; k < (St::ROWS / 2 + GC - 1) / GC; ++k) {
+                    const int i = g.gl + k * GC;
+                    if (i < St::ROWS / 2) __stcs(d_tgt + i, reinterpret_cast<const int4 *>(stage)[i]);
+                }
             }
         }
         return;
