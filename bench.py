@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--cpu-envs", type=int, default=8192, help="sample size (envs) of the CPU legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (solver kernel, configs[2])")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--seed", type=int, default=20261018)
     return ap.parse_args()
@@ -69,6 +70,41 @@ def cpu_rollout_rate(variant, n_envs, steps, threads, seed, policy="random", war
     return agent_steps / dt, dt, agent_steps
 
 
+def _python_port_worker(job):
+    """One reference-style env object (numpy port of core.py) stepped in a Python loop."""
+    variant, seconds, seed = job
+    import numpy as np
+    from oracle import ref_port as rp
+    from oracle import wh_oracle as wo
+    v = wo.VARIANTS[variant]
+    A = v["num_requests"]
+    env = rp.PortWarehouse(A, v["num_requests"], v["area_dimension"], v["racks"], rng=np.random.default_rng(seed))
+    env.reset()
+    rng = np.random.default_rng(seed + 1)
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        for _ in range(50):
+            acts = rng.integers(0, 9, size=A)
+            _, _, done = env.step(list(enumerate(acts.tolist())))
+            n += 1
+            if done:
+                env.reset()
+    return n * A, time.perf_counter() - t0
+
+
+def python_port_baseline(variant, seconds, seed):
+    """The reference's own cost class: Python + numpy, one env object per process (what RLlib's
+    MultiAgentEnv->BaseEnv vectorisation loops over), on every host core."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    with mp.get_context("spawn").Pool(cores) as pool:
+        res = pool.map(_python_port_worker, [(variant, seconds, seed + 17 * i) for i in range(cores)])
+    rate = sum(n / dt for n, dt in res)
+    return {"value": rate, "unit": "agent-steps/s", "cores": cores, "kind": "port",
+            "sample": f"oracle/ref_port.py (numpy port at the reference's granularity), 1 {variant} env per process x "
+                      f"{cores} processes, {seconds:.0f}s each, random actions"}
+
+
 def cpu_baseline(args, budget_s):
     threads = os.cpu_count() or 1
     n = args.cpu_envs
@@ -76,11 +112,16 @@ def cpu_baseline(args, budget_s):
     steps = max(8, int(budget_s * rate / (n * VARIANT_AGENTS[args.variant])))
     steps = min(steps, 4000)
     rate, dt, agent_steps = cpu_rollout_rate(args.variant, n, steps, threads, args.seed, "random")
-    return {
+    out = {
         "value": rate, "unit": "agent-steps/s", "cores": threads, "kind": "port",
         "sample": f"oracle/wh_oracle.c (C port of core.py step+obs), {n} {args.variant} envs x {steps} steps, "
                   f"random actions, {threads} pthreads, {dt:.1f}s",
     }
+    try:
+        out["python_port"] = python_port_baseline(args.variant, 4.0, args.seed)
+    except Exception as e:  # noqa: BLE001
+        out["python_port"] = {"error": repr(e)}
+    return out
 
 
 def run_reference(args):
@@ -318,6 +359,8 @@ def run_b200(args):
         out["gpu_launches_e2e"] = int(L.wh_env_launch_count(h))
         L.wh_env_destroy(h)
 
+    if world == 1 and not args.no_extras:
+        out["extras"] = extras(args, dev, peak)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, args.cpu_seconds)
     out["stats"] = {k: v for k, v in env.stats_dict(stats).items() if not k.startswith("avg_agent_reward_") or k.endswith("_all")}
@@ -326,6 +369,50 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _time_steps(fn, steps, warmup):
+    import torch
+    for i in range(warmup):
+        fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def extras(args, dev, peak):
+    """Secondary lines (not the headline): the solver kernel's own roofline, the run.py-style loop
+    (solver kernel + step kernel), the single fused kernel, and BASELINE configs[2]
+    (Medium, 65 536 envs, batched greedy solver)."""
+    import torch
+    from rllib_warehouse_b200 import VARIANTS, BatchedWarehouse
+    res = {}
+    for name, variant, n in (("large_262144", "large", args.envs if args.variant == "large" else 262144),
+                             ("configs2_medium_65536", "medium", 65536)):
+        A = VARIANT_AGENTS[variant]
+        env = BatchedWarehouse(VARIANTS[variant], n, device=dev, seed=args.seed + 1, auto_reset=True)
+        env.reset()
+        steps, warm = 100, 10
+        ms_solver = _time_steps(lambda i: env.greedy_actions(), steps, warm)
+        ms_loop = _time_steps(lambda i: env.step(env.greedy_actions()), steps, warm)
+        ms_fused = _time_steps(lambda i: env.greedy_step(want_actions=False), steps, warm)
+        sb = SOLVER_BYTES_PER_AGENT[variant] * n * A
+        fb = ALG_BYTES_PER_ENV_STEP[variant] * n
+        res[name] = {
+            "solver_kernel": {"ms": ms_solver, "achieved_GBs": sb / ms_solver / 1e6, "frac": sb / ms_solver / 1e6 / peak,
+                              "alg_bytes_per_launch": sb},
+            "solver_plus_step": {"ms": ms_loop, "agent_steps_per_sec": n * A / (ms_loop * 1e-3), "launches_per_step": 2},
+            "fused_greedy_step": {"ms": ms_fused, "agent_steps_per_sec": n * A / (ms_fused * 1e-3),
+                                  "frac": fb / ms_fused / 1e6 / peak, "launches_per_step": 1},
+        }
+        del env
+        torch.cuda.empty_cache()
+    return res
 
 
 def main():

@@ -12,7 +12,7 @@
  *
  * Conventions
  *  - extern "C", plain pointers and sizes only. No torch / C++ types cross this boundary.
- *  - Layer 1 (wh_reset / wh_step / wh_build_obs / wh_greedy / wh_rollout): every data pointer is a
+ *  - Layer 1 (wh_reset / wh_step / wh_build_obs / wh_greedy / wh_greedy_step): every data pointer is a
  *    DEVICE pointer owned by the caller (e.g. a torch CUDA tensor); the functions launch sm_100a
  *    kernels on `stream` (a cudaStream_t passed as void*, NULL = default stream), never allocate,
  *    never synchronise, and return 0 or a non-zero error code (cudaError_t value, or WH_E_* below).
@@ -38,6 +38,7 @@ extern "C" {
 /* error codes outside the cudaError_t range */
 #define WH_E_CONFIG 10001     /* unsupported configuration (limits below) */
 #define WH_E_ARG    10002     /* NULL / inconsistent arguments */
+#define WH_E_NCCL   10003     /* ncclAllReduce not resolvable in this process / NCCL error (code - 11000) */
 
 /* Limits: R <= 32, P = 4*L*L <= 64 (L <= 4), D = 4*(dim-4) <= 64 (dim <= 20), dim <= 127.
  * All six reference variants (variants.py:19-98) are inside them. */
@@ -115,6 +116,13 @@ int wh_step(const wh_config *cfg, const wh_state *st, int64_t n_envs, int64_t en
 int wh_build_obs(const wh_config *cfg, const wh_state *st, int64_t n_envs, int flavour,
                  const wh_obs *obs, void *stream);
 
+/* Observations in RLlib's flattened layout (what RLlib's Dict preprocessor would build from the
+ * core.py:119-148 space): float32 out[N, R, 9R+1], keys concatenated in alphabetical order
+ * num_agents(1) other_availabilities(R-1) other_delivery_targets(2(R-1)) other_positions(2(R-1))
+ * requests(4R) self_availability(1) self_delivery_target(2) self_position(2). */
+int wh_build_obs_flat(const wh_config *cfg, const wh_state *st, int64_t n_envs, int flavour,
+                      float *out, void *stream);
+
 /* WarehouseRandomGreedySolver.compute_action — solvers.py:27-58 — on observation tensors.
  * rand_threshold = floor(random_action_prob * 2^32). is_random / random_actions [N,R] replay the
  * eps-random branch (solvers.py:44-45); NULL = native RNG keyed by (seed, env, episode, time, agent).
@@ -131,6 +139,12 @@ int wh_greedy_step(const wh_config *cfg, const wh_state *st, int64_t n_envs, int
                    uint64_t seed, uint64_t solver_seed, uint64_t rand_threshold,
                    int32_t *actions_out, float *rewards, uint8_t *dones,
                    unsigned long long *stats, const wh_obs *obs, int flags, void *stream);
+
+/* End-of-rollout reduction of the episode statistics over NVLink: in-place ncclAllReduce(sum) of the
+ * WH_NUM_STATS uint64 counters on `stream`. `nccl_comm` is a ncclComm_t created by the caller with
+ * the NCCL already loaded in the process (the symbol is resolved at run time with dlsym, so the
+ * library has no link-time NCCL dependency). This is the only collective on the path. */
+int wh_stats_allreduce(unsigned long long *stats, void *nccl_comm, void *stream);
 
 /* ---- Layer 2: host-buffer environment handle -------------------------------------------- */
 typedef struct wh_env wh_env;

@@ -11,11 +11,12 @@ from .core import Warehouse
 from .variants import (WarehouseLarge, WarehouseLargeTrain, WarehouseMedium, WarehouseMediumTrain,
                        WarehouseSmall, WarehouseSmallTrain)
 from .solvers import BatchedGreedySolver, WarehouseRandomGreedySolver, WarehouseSolver
+from .vector_env import WarehouseVectorEnv
 
 __all__ = [
     "Warehouse", "WarehouseSmall", "WarehouseMedium", "WarehouseLarge",
     "WarehouseSmallTrain", "WarehouseMediumTrain", "WarehouseLargeTrain",
     "WarehouseConfig", "SMALL", "MEDIUM", "LARGE", "VARIANTS",
-    "BatchedWarehouse", "BatchedGreedySolver", "WarehouseRandomGreedySolver", "WarehouseSolver",
+    "BatchedWarehouse", "WarehouseVectorEnv", "BatchedGreedySolver", "WarehouseRandomGreedySolver", "WarehouseSolver",
 ]
 name = "rllib_warehouse_b200"

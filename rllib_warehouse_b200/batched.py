@@ -154,6 +154,30 @@ class BatchedWarehouse:
         self.launches += 1
         return self.obs
 
+    def build_obs_flat(self, flavour=None, out=None):
+        """Observations in RLlib's flattened float32 layout [N, R, 9R+1] (alphabetical key order of
+        the core.py:119-148 Dict space), written by one kernel straight from the resident state.
+        flavour: OBS_STEP (default) or OBS_RESET, as for build_obs."""
+        N, R = self.N, self.R
+        if out is None:
+            if getattr(self, "_flat", None) is None:
+                self._flat = torch.empty((N, R, 9 * R + 1), dtype=torch.float32, device=self.device)
+            out = self._flat
+        with torch.cuda.device(self.device):
+            rc = self.lib.wh_build_obs_flat(C.byref(self._cfg), C.byref(self._st), N,
+                                            nv.OBS_STEP if flavour is None else int(flavour),
+                                            out.data_ptr(), self._stream())
+        nv.check(rc, "wh_build_obs_flat")
+        self.launches += 1
+        return out
+
+    @staticmethod
+    def flatten_obs(obs):
+        """Reference flattening of the dict observations (RLlib Dict preprocessor order)."""
+        keys = sorted(obs.keys())
+        n, r = obs["requests"].shape[:2]
+        return torch.cat([obs[k].reshape(n, r, -1).to(torch.float32) for k in keys], dim=2)
+
     def greedy_actions(self, obs=None, random_action_prob=0.0, solver_seed=0, is_random=None,
                        random_actions=None, out=None):
         """solvers.py:27-58 on observation tensors (defaults to the resident observations)."""

@@ -12,7 +12,7 @@ SOURCES = ["wh_b200.cu"]
 DEPS = ["wh_b200.cu", "wh_kernels.cuh", os.path.join("..", "..", "include", "wh_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v",
+    "-shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-ldl",
 ]
 
 

@@ -5,6 +5,8 @@
 #include <cstring>
 #include <new>
 
+#include <dlfcn.h>
+
 #include "wh_kernels.cuh"
 
 namespace wh {
@@ -133,31 +135,88 @@ __global__ void __launch_bounds__(BLOCK) k_obs(const __grid_constant__ KParams P
     build_obs<GC, RC>(P, g, t.e, R, s, active, target_cell16(P, s.atgt), P.flavour, t.live, StageMem<GC, RC>::mine(smem, g));
 }
 
+// RLlib-flattened float32 observations from the resident state
+template <int GC, int RC>
+__global__ void __launch_bounds__(BLOCK) k_obs_flat(const __grid_constant__ KParams P) {
+    constexpr int EPW = GC ? 32 / GC : 1;
+    __shared__ __align__(16) unsigned char smem[RC ? (BLOCK / 32) * EPW * FlatStage<RC>::BYTES : 16];
+    const Group<GC> g(P.G);
+    const Tile<GC> t(P, g);
+    const int R = RC ? RC : P.R;
+    EnvRegs s;
+    load_env(P, g, t.e, R, s);
+    const unsigned long long active = active_mask(g, s.pt4);
+    float *stage = nullptr;
+    if (RC) stage = reinterpret_cast<float *>(smem + ((threadIdx.x >> 5) * EPW + (g.ghost ? 0 : g.gi)) * FlatStage<RC>::BYTES);
+    build_obs_flat<GC, RC>(P, g, t.e, R, s, active, target_cell16(P, s.atgt), P.flavour, t.live,
+                           reinterpret_cast<float *>(P.rewards), stage);
+}
+
 // WarehouseRandomGreedySolver.compute_action on observation tensors — solvers.py:27-58.
-// One group of R lanes per AGENT ROW: lane r loads request r with one 128-bit load (16R contiguous
-// bytes per row); the L1 argmin with first-minimum tie-break is a min-reduction over
-// (distance<<8 | r) inside the group.
-template <int RC>
+// LR lanes cooperate on one AGENT ROW (4 for Large, 3 for Medium, 1 for Small): lane j loads
+// requests j, j+LR, ... with 128-bit loads (each load instruction covers 16*LR contiguous bytes of
+// every row in the warp, all loads of a lane are issued back to back), keeps its running
+// (distance<<8 | r) minimum, and the LR partial minima are combined by shuffles: the L1 argmin with
+// first-minimum tie-break of solvers.py:53-58.
+template <int RC, int LR>
 __global__ void __launch_bounds__(BLOCK) k_greedy(const __grid_constant__ KParams P) {
     const int R = RC ? RC : P.R;
-    const Group<RC> g(R);
+    constexpr int RPW = 32 / LR;                       // agent rows per warp
+    const int lane = threadIdx.x & 31, gi = lane / LR, j = lane - gi * LR;
+    const bool ghost = gi >= RPW;
     const long long rows = P.N * R;
     const long long warp = ((long long)blockIdx.x * BLOCK + threadIdx.x) >> 5;
-    const long long row_raw = warp * g.epw + g.gi;
-    const bool live = !g.ghost && row_raw < rows;
+    const long long row_raw = warp * RPW + gi;
+    const bool live = !ghost && row_raw < rows;
     const long long row = row_raw < rows ? row_raw : rows - 1;
     const long long e = row / R;
     const int a = (int)(row - e * R);
     const wh_obs &o = P.obs;
-    const int4 rq = __ldcs(reinterpret_cast<const int4 *>(o.requests) + row * R + g.gl);
+    const int4 *req = reinterpret_cast<const int4 *>(o.requests) + row * R;
     const int2 sp = reinterpret_cast<const int2 *>(o.self_position)[row];
     const int2 stg = reinterpret_cast<const int2 *>(o.self_delivery_target)[row];
     const int avail = o.self_availability[row];
     const int A = P.g_num_agents[e];
-    const int d = abs(sp.x - rq.x) + abs(sp.y - rq.y);                         // solvers.py:54-57
-    const uint32_t best = g.min_u32(((uint32_t)d << 8) | (uint32_t)g.gl);      // solvers.py:58 argmin
-    const uint32_t cell = g.shfl((uint32_t)(rq.x & 0xFFFF) | ((uint32_t)rq.y << 16), (int)(best & 0xFFu));
-    int tx = (int)(cell & 0xFFFF), ty = (int)(cell >> 16);
+    uint32_t best = 0xffffffffu, bcell = 0;
+    constexpr int RPL = RC ? (RC + LR - 1) / LR : 1;   // requests per lane (compile-time R)
+    if (RC) {
+        int4 rq[RPL];
+#pragma unroll
+        for (int k = 0; k < RPL; ++k) {
+            const int r = j + k * LR;
+            rq[k] = (r < RC) ? __ldcs(req + r) : make_int4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int k = 0; k < RPL; ++k) {
+            const int r = j + k * LR;
+            const uint32_t key = (r < RC) ? (((uint32_t)(abs(sp.x - rq[k].x) + abs(sp.y - rq[k].y)) << 8) | (uint32_t)r)
+                                          : 0xffffffffu;                       // solvers.py:54-57
+            if (key < best) { best = key; bcell = (uint32_t)(rq[k].x & 0xFFFF) | ((uint32_t)rq[k].y << 16); }
+        }
+    } else {
+        for (int r = j; r < R; r += LR) {
+            const int4 q = __ldcs(req + r);
+            const uint32_t key = ((uint32_t)(abs(sp.x - q.x) + abs(sp.y - q.y)) << 8) | (uint32_t)r;
+            if (key < best) { best = key; bcell = (uint32_t)(q.x & 0xFFFF) | ((uint32_t)q.y << 16); }
+        }
+    }
+    if (LR == 2 || LR == 4) {                                                  // solvers.py:58 argmin
+#pragma unroll
+        for (int m = 1; m < LR; m <<= 1) {
+            const uint32_t ob = __shfl_xor_sync(FULL, best, m), oc = __shfl_xor_sync(FULL, bcell, m);
+            if (ob < best) { best = ob; bcell = oc; }
+        }
+    } else if (LR > 1) {
+        const int base = ghost ? 0 : gi * LR;
+        uint32_t b0 = best, c0 = bcell;
+#pragma unroll
+        for (int k = 0; k < LR; ++k) {
+            const uint32_t ob = __shfl_sync(FULL, best, base + k), oc = __shfl_sync(FULL, bcell, base + k);
+            if (ob < b0) { b0 = ob; c0 = oc; }
+        }
+        best = b0; bcell = c0;
+    }
+    int tx = (int)(bcell & 0xFFFF), ty = (int)(bcell >> 16);
     if (avail == 0) { tx = stg.x; ty = stg.y; }                                 // solvers.py:33-34
     const int sx = max(-1, min(1, tx - sp.x)), sy = max(-1, min(1, ty - sp.y)); // solvers.py:41
     int action = (sx + 1) * 3 + (sy + 1);                                      // solvers.py:47-49
@@ -169,7 +228,7 @@ __global__ void __launch_bounds__(BLOCK) k_greedy(const __grid_constant__ KParam
                       (uint32_t)a, P.solver_seed, u0, u1);
         if ((unsigned long long)u0 < P.rand_thr) action = (int)bounded(u1, 9u);
     }
-    if (live && g.gl == 0) P.actions_out[row] = (a < A) ? action : -1;
+    if (live && j == 0) P.actions_out[row] = (a < A) ? action : -1;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -221,7 +280,7 @@ static bool obs_ok(const wh_obs *o) {
            o->other_positions && o->other_availabilities && o->other_delivery_targets && o->requests;
 }
 
-enum Kind { K_STEP, K_GSTEP, K_RESET, K_OBS, K_GREEDY };
+enum Kind { K_STEP, K_GSTEP, K_RESET, K_OBS, K_OBS_FLAT, K_GREEDY };
 
 template <int GC, int RC>
 static void launch_kind(Kind kind, const KParams &K, cudaStream_t s) {
@@ -233,25 +292,26 @@ static void launch_kind(Kind kind, const KParams &K, cudaStream_t s) {
     case K_GSTEP: k_step<GC, RC, true><<<grid, BLOCK, 0, s>>>(K); break;
     case K_RESET: k_reset<GC, RC><<<grid, BLOCK, 0, s>>>(K); break;
     case K_OBS: k_obs<GC, RC><<<grid, BLOCK, 0, s>>>(K); break;
+    case K_OBS_FLAT: k_obs_flat<GC, RC><<<grid, BLOCK, 0, s>>>(K); break;
     default: break;
     }
 }
 
-template <int RC>
+template <int RC, int LR>
 static void launch_greedy(const KParams &K, cudaStream_t s) {
-    const long long rpw = 32 / K.R, warps = (K.N * K.R + rpw - 1) / rpw;   // agent rows per warp
+    const long long rpw = 32 / LR, warps = (K.N * K.R + rpw - 1) / rpw;   // agent rows per warp
     const unsigned grid = (unsigned)((warps * 32 + BLOCK - 1) / BLOCK);
-    k_greedy<RC><<<grid, BLOCK, 0, s>>>(K);
+    k_greedy<RC, LR><<<grid, BLOCK, 0, s>>>(K);
 }
 
 static int launch(Kind kind, const KParams &K, const Shape &sh, void *stream) {
     if (K.N <= 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     if (kind == K_GREEDY) {
-        if (sh.RC == 4) launch_greedy<4>(K, s);
-        else if (sh.RC == 9) launch_greedy<9>(K, s);
-        else if (sh.RC == 16) launch_greedy<16>(K, s);
-        else launch_greedy<0>(K, s);
+        if (K.R == 4) launch_greedy<4, 1>(K, s);
+        else if (K.R == 9) launch_greedy<9, 3>(K, s);
+        else if (K.R == 16) launch_greedy<16, 4>(K, s);
+        else launch_greedy<0, 4>(K, s);
     } else if (sh.RC == 4) launch_kind<4, 4>(kind, K, s);
     else if (sh.RC == 9) launch_kind<9, 9>(kind, K, s);
     else if (sh.RC == 16) launch_kind<16, 16>(kind, K, s);
@@ -274,6 +334,8 @@ const char *wh_error_string(int code) {
     if (code == 0) return "ok";
     if (code == WH_E_CONFIG) return "unsupported warehouse configuration (limits: 2<=R<=32, P<=64, D<=64, dim<=127)";
     if (code == WH_E_ARG) return "NULL or inconsistent argument";
+    if (code == WH_E_NCCL) return "ncclAllReduce could not be resolved in this process (load NCCL first)";
+    if (code > 11000 && code < 11100) return "NCCL error (code - 11000 = ncclResult_t)";
     return cudaGetErrorString((cudaError_t)code);
 }
 
@@ -338,6 +400,17 @@ int wh_build_obs(const wh_config *cfg, const wh_state *st, int64_t n_envs, int f
     return launch(K_OBS, K, sh, stream);
 }
 
+int wh_build_obs_flat(const wh_config *cfg, const wh_state *st, int64_t n_envs, int flavour,
+                      float *out, void *stream) {
+    KParams K; Shape sh;
+    if (int rc = fill_params(cfg, K, sh)) return rc;
+    if (!state_ok(st) || !out || (flavour != WH_OBS_STEP && flavour != WH_OBS_RESET)) return WH_E_ARG;
+    set_state(K, st);
+    K.rewards = out;   // the flat output travels in the `rewards` slot of the launch parameters
+    K.N = n_envs; K.flavour = flavour;
+    return launch(K_OBS_FLAT, K, sh, stream);
+}
+
 int wh_greedy(const wh_config *cfg, const wh_obs *obs, const int8_t *num_agents,
               const int32_t *episode, const int32_t *time, int64_t n_envs, int64_t env_id0,
               uint64_t seed, uint64_t rand_threshold, const uint8_t *is_random,
@@ -353,6 +426,24 @@ int wh_greedy(const wh_config *cfg, const wh_obs *obs, const int8_t *num_agents,
     K.is_random = is_random; K.random_actions = random_actions; K.g_num_agents = num_agents;
     K.g_episode = episode; K.g_time = time; K.actions_out = actions;
     return launch(K_GREEDY, K, sh, stream);
+}
+
+int wh_stats_allreduce(unsigned long long *stats, void *nccl_comm, void *stream) {
+    if (!stats || !nccl_comm) return WH_E_ARG;
+    // ncclResult_t ncclAllReduce(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t)
+    typedef int (*allreduce_fn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+    static allreduce_fn fn = nullptr;
+    if (!fn) {
+        fn = (allreduce_fn)dlsym(RTLD_DEFAULT, "ncclAllReduce");
+        if (!fn) {
+            void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+            if (h) fn = (allreduce_fn)dlsym(h, "ncclAllReduce");
+        }
+        if (!fn) return WH_E_NCCL;
+    }
+    const int ncclUint64 = 5, ncclSum = 0;   // nccl.h enums (stable since NCCL 2.0)
+    const int rc = fn(stats, stats, WH_NUM_STATS, ncclUint64, ncclSum, nccl_comm, (cudaStream_t)stream);
+    return rc == 0 ? 0 : 11000 + rc;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -587,6 +587,101 @@ __device__ __forceinline__ void build_obs(const KParams &P, const Group<GC> &g, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// RLlib-flattened observations: float32 [N, R, 9R+1], keys in RLlib's Dict
+// flattening order (alphabetical): num_agents(1) other_availabilities(R-1)
+// other_delivery_targets(2(R-1)) other_positions(2(R-1)) requests(4R) self_availability(1)
+// self_delivery_target(2) self_position(2). Same values as build_obs (core.py:371-432 / 224-260).
+// ---------------------------------------------------------------------------------------------
+template <int RC>
+struct FlatStage {
+    static constexpr int F = 9 * RC + 1;                                     // floats per agent row
+    static constexpr int VEC = RC == 0 ? 1 : ((RC * F) % 4 == 0 ? 4 : ((RC * F) % 2 == 0 ? 2 : 1));
+    // rows per staged chunk: chunk floats must be a multiple of VEC
+    static constexpr int CHUNK = RC == 0 ? 1 : ((F % VEC == 0) ? (RC < 4 ? RC : 4) : ((2 * F) % VEC == 0 ? 2 : 4));
+    static constexpr int BYTES = RC ? ((CHUNK * F * 4 + 15) / 16) * 16 : 16;
+};
+
+template <int GC, int RC>
+__device__ __forceinline__ void build_obs_flat(const KParams &P, const Group<GC> &g, long long e, int R,
+                                               const EnvRegs &s, unsigned long long active, uint32_t tpos16,
+                                               int flavour, bool live, float *out, float *stage) {
+    constexpr bool WIDE = Group<GC>::WIDE;
+    const int null_pos = P.null_pos;
+    const uint32_t null16 = (uint32_t)null_pos | ((uint32_t)null_pos << 8);
+    const bool real = g.gl < s.A;
+    const bool delivering = real && s.atgt > -1;
+    const uint32_t ppos = real ? s.pos16 : null16;
+    const uint32_t avail = (flavour == WH_OBS_STEP && real && !delivering) ? 1u : 0u;
+    const uint32_t tpos = (flavour == WH_OBS_STEP && delivering) ? tpos16 : null16;
+    const uint32_t mine = (ppos & 0x7Fu) | (((ppos >> 8) & 0x7Fu) << 7) | ((tpos & 0x7Fu) << 14) |
+                          (((tpos >> 8) & 0x7Fu) << 21) | (avail << 28);
+    const uint32_t next = g.shfl_down1(mine);
+    const bool have = g.gl < R && g.gl < __popcll(active);
+    const int p = nth_set64<WIDE>(active, have ? g.gl : 0) & 63;
+    const uint32_t w4 = g.shfl(s.pt4, p >> 2);
+    float4 rq = make_float4((float)null_pos, (float)null_pos, (float)null_pos, (float)null_pos);
+    if (have) {
+        const uint32_t pc = pickup_cell16(P, p);
+        const uint32_t dc = delivery_cell16((int)((w4 >> (8 * (p & 3))) & 0x3Fu), P.dim);
+        rq = make_float4((float)(pc & 0xFF), (float)(pc >> 8), (float)(dc & 0xFF), (float)(dc >> 8));
+    }
+    const int F = 9 * R + 1;
+    const float n_agents = (float)s.A;
+    const bool writer = !g.ghost;
+    auto px = [](uint32_t v) { return (float)(v & 0x7F); };
+    auto py = [](uint32_t v) { return (float)((v >> 7) & 0x7F); };
+    auto tx = [](uint32_t v) { return (float)((v >> 14) & 0x7F); };
+    auto ty = [](uint32_t v) { return (float)((v >> 21) & 0x7F); };
+    auto av = [](uint32_t v) { return (float)((v >> 28) & 1); };
+    const uint32_t t_row1 = (g.gl >= 1) ? next : mine;       // core.py:428 (step) drops row 1
+    // writes agent row `a` of this env at dst[0 .. F)
+    auto emit_row = [&](float *dst, int a) {
+        if (g.gl == 0) dst[0] = n_agents;
+        if (g.gl < R - 1) {
+            const uint32_t o = (g.gl >= a) ? next : mine;                       // core.py:426-427
+            const uint32_t t = (flavour == WH_OBS_STEP) ? t_row1 : o;
+            dst[1 + g.gl] = av(o);
+            dst[R + 2 * g.gl] = tx(t); dst[R + 2 * g.gl + 1] = ty(t);
+            dst[3 * R - 2 + 2 * g.gl] = px(o); dst[3 * R - 2 + 2 * g.gl + 1] = py(o);
+        }
+        if (g.gl < R) {
+            float *q = dst + 5 * R - 4 + 4 * g.gl;
+            q[0] = rq.x; q[1] = rq.y; q[2] = rq.z; q[3] = rq.w;
+        }
+        if (g.gl == a) {
+            dst[9 * R - 4] = av(mine);
+            dst[9 * R - 3] = tx(mine); dst[9 * R - 2] = ty(mine);
+            dst[9 * R - 1] = px(mine); dst[9 * R] = py(mine);
+        }
+    };
+    float *env_out = out + e * (long long)R * F;
+    if constexpr (RC != 0) {
+        using St = FlatStage<RC>;
+#pragma unroll
+        for (int a0 = 0; a0 < RC; a0 += St::CHUNK) {
+            const int rows = (RC - a0 < St::CHUNK) ? RC - a0 : St::CHUNK;
+#pragma unroll
+            for (int la = 0; la < St::CHUNK; ++la)
+                if (la < rows && writer) emit_row(stage + la * St::F, a0 + la);
+            __syncwarp();
+            if (live) {
+                const int nvec = rows * St::F / St::VEC;
+                float *dst = env_out + a0 * St::F;
+                for (int i = g.gl; i < nvec; i += GC) {
+                    if (St::VEC == 4) __stcs(reinterpret_cast<float4 *>(dst) + i, reinterpret_cast<const float4 *>(stage)[i]);
+                    else if (St::VEC == 2) __stcs(reinterpret_cast<float2 *>(dst) + i, reinterpret_cast<const float2 *>(stage)[i]);
+                    else __stcs(dst + i, stage[i]);
+                }
+            }
+            __syncwarp();
+        }
+    } else {
+        if (live)
+            for (int a = 0; a < R; ++a) emit_row(env_out + a * F, a);
+    }
+}
+
 // delivery-target cell of my agent for the observation tables (null cell when not delivering)
 __device__ __forceinline__ uint32_t target_cell16(const KParams &P, int atgt) {
     return atgt > -1 ? delivery_cell16(atgt, P.dim) : ((uint32_t)P.null_pos | ((uint32_t)P.null_pos << 8));

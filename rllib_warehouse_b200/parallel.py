@@ -53,3 +53,45 @@ def stats_to_metrics(stats, max_agents: int):
     if s[0]:
         out["avg_agent_reward_all"] = num / s[0]
     return out
+
+
+class RawNcclStats:
+    """The same reduction through the C ABI (`wh_stats_allreduce`) on a raw `ncclComm_t`, i.e. what
+    a non-PyTorch host program would do. The communicator is created here with the NCCL that
+    PyTorch already loaded (unique id broadcast over the existing torch.distributed group)."""
+
+    def __init__(self, device):
+        import ctypes as C
+        self.C, self.device = C, torch.device(device)
+        self.nccl = C.CDLL("libnccl.so.2")
+        rank, world = dist.get_rank(), dist.get_world_size()
+
+        class UniqueId(C.Structure):
+            _fields_ = [("internal", C.c_byte * 128)]
+
+        uid = UniqueId()
+        if rank == 0:
+            rc = self.nccl.ncclGetUniqueId(C.byref(uid))
+            assert rc == 0, rc
+        t = torch.tensor(list(bytes(uid)), dtype=torch.uint8, device=self.device)
+        dist.broadcast(t, src=0)
+        C.memmove(C.byref(uid), bytes(t.cpu().tolist()), 128)
+        self.comm = C.c_void_p()
+        self.nccl.ncclCommInitRank.argtypes = [C.c_void_p, C.c_int, UniqueId, C.c_int]
+        with torch.cuda.device(self.device):
+            rc = self.nccl.ncclCommInitRank(C.byref(self.comm), world, uid, rank)
+        assert rc == 0, f"ncclCommInitRank -> {rc}"
+
+    def allreduce(self, stats: torch.Tensor) -> torch.Tensor:
+        out = stats.clone()
+        with torch.cuda.device(self.device):
+            rc = nv.lib().wh_stats_allreduce(out.data_ptr(), self.comm,
+                                             torch.cuda.current_stream(self.device).cuda_stream)
+        nv.check(rc, "wh_stats_allreduce")
+        return out
+
+    def close(self):
+        if self.comm:
+            self.nccl.ncclCommDestroy.argtypes = [self.C.c_void_p]
+            self.nccl.ncclCommDestroy(self.comm)
+            self.comm = None

@@ -184,3 +184,28 @@ def test_philox_matches_oracle():
         c = wo.OracleEnv(wo.variant_config("small"), 3, seed=seed, env_id0=eid)
         g.reset(); c.reset()
         same_state(g, c, f"seed {seed}")
+
+
+@pytest.mark.parametrize("size", list(SIZES))
+def test_flat_observations(size):
+    """RLlib-flattened float32 observations == the (oracle-verified) dict observations flattened in
+    alphabetical key order, for both flavours and per-env agent counts."""
+    from rllib_warehouse_b200 import VARIANTS, BatchedWarehouse
+    from rllib_warehouse_b200 import _native as nv
+    n = 1000
+    env = BatchedWarehouse(VARIANTS[size].replace(random_num_agents=True), n, seed=4)
+    obs = env.reset()
+    flat = env.build_obs_flat(nv.OBS_RESET)
+    assert flat.shape == (n, env.R, 9 * env.R + 1) and flat.dtype == torch.float32
+    assert torch.equal(flat, env.flatten_obs(obs))
+    for t in range(30):
+        obs, _, _ = env.greedy_step()
+        if t % 5 == 0:
+            assert torch.equal(env.build_obs_flat(), env.flatten_obs(obs)), t
+    cfgs = [(6, 14, (3, 7, 11)), (3, 11, (5,))]
+    from rllib_warehouse_b200 import WarehouseConfig
+    for R, dim, racks in cfgs:           # runtime-R path
+        env = BatchedWarehouse(WarehouseConfig(R, dim, racks, 40, 25, R), 77, seed=1)
+        env.reset()
+        obs, _, _ = env.greedy_step()
+        assert torch.equal(env.build_obs_flat(), env.flatten_obs(obs))

@@ -104,3 +104,58 @@ def test_greedy_returns_match_reference_statistics():
         ret = (env.state["acc"][:, 0] + env.state["acc"][:, 1]).double()
         assert abs(ret.mean().item() - mean) < 4 * std / np.sqrt(200), (size, ret.mean().item())
         assert abs(ret.std().item() - std) < 0.2 * std, (size, ret.std().item())
+
+
+@pytest.mark.parametrize("flat", [False, True])
+def test_vector_env_base_env_protocol(flat):
+    """poll / send_actions / try_reset (RLlib BaseEnv protocol) against a BatchedWarehouse twin."""
+    import torch
+    from rllib_warehouse_b200 import MEDIUM, BatchedWarehouse, WarehouseVectorEnv
+    from rllib_warehouse_b200 import _native as nv
+    n, A = 7, 5
+    venv = WarehouseVectorEnv(MEDIUM, n, num_agents=A, seed=42, flat_obs=flat)
+    twin = BatchedWarehouse(MEDIUM, n, num_agents=A, seed=42)
+    twin.reset()
+
+    def expect(e, i, flavour):
+        if flat:
+            return twin.build_obs_flat(flavour)[e, i].cpu().numpy()
+        return {k: twin.obs[k][e, i].cpu().numpy() for k in twin.obs}
+
+    def same(a, b):
+        if flat:
+            return np.array_equal(a, b)
+        return set(a) == set(b) and all(np.array_equal(a[k], b[k]) for k in a)
+
+    obs, rew, dones, infos, off = venv.poll()
+    assert sorted(obs) == list(range(n)) and off == {}
+    assert all(rew[e][str(i)] is None and not dones[e]["__all__"] for e in obs for i in range(A))
+    assert all(same(obs[e][str(i)], expect(e, i, nv.OBS_RESET)) for e in range(n) for i in range(A))
+    rng = np.random.Generator(np.random.PCG64(0))
+    resets = 0
+    for t in range(203):
+        acts = {e: {str(i): int(rng.integers(0, 9)) for i in (range(A) if e % 2 else reversed(range(A)))} for e in range(n)}
+        venv.send_actions(acts)
+        a = np.full((n, twin.R), -1, np.int32); order = np.full((n, twin.R), -1, np.int32)
+        for e in range(n):
+            for k, (ag, v) in enumerate(acts[e].items()):
+                a[e, int(ag)] = v; order[e, k] = int(ag)
+        twin.step(a, order=order)
+        obs, rew, dones, infos, _ = venv.poll()
+        assert venv.poll()[0] == {}                                   # nothing pending until the next send
+        for e in range(n):
+            assert dones[e]["__all__"] == bool(twin.dones[e].item())
+            for i in range(A):
+                assert rew[e][str(i)] == twin.rewards[e, i].item()
+                assert same(obs[e][str(i)], expect(e, i, nv.OBS_STEP)), (t, e, i)
+            if dones[e]["__all__"] and e < 3:                          # reset some of the finished envs
+                mask = np.zeros(n, np.uint8); mask[e] = 1
+                twin.reset(env_mask=mask)
+                fresh = venv.try_reset(e)
+                assert all(same(fresh[str(i)], expect(e, i, nv.OBS_RESET)) for i in range(A))
+                resets += 1
+    assert resets >= 3
+    # tensor API
+    o = venv.reset_tensors()
+    o2, r2, d2 = venv.step_tensors(torch.zeros((n, twin.R), dtype=torch.int32, device="cuda"))
+    assert r2.shape == (n, twin.R) and d2.shape == (n,)
