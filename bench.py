@@ -308,9 +308,16 @@ def run_b200(args):
         peak = 6650.0
     alg_bytes = ALG_BYTES_PER_ENV_STEP[args.variant] * n_local
     achieved = alg_bytes / (k_avg_ms * 1e-3) / 1e9
+    traffic = None
+    try:   # ncu-measured DRAM bytes per launch for this exact launch shape (profiles/, round 1)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[args.variant]
+        if tj["envs_per_launch"] == n_local:
+            traffic = tj["traffic_bytes"]
+    except Exception:  # noqa: BLE001
+        pass
     roofline = {
         "bound": "hbm", "kernel": "wh::k_step (fused step + observation build)", "achieved": achieved,
-        "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
         "alg_bytes_per_launch": alg_bytes, "kernel_ms_avg": k_avg_ms, "kernel_ms_median": kms[len(kms) // 2],
         "peak_source": peak_src,
     }

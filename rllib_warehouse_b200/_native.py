@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libwh_b200.so")
+LIB_PATH = os.environ.get("WH_B200_LIB") or os.path.join(HERE, "lib", "libwh_b200.so")   # env override: kernel tuning builds
 MAX_RACKS = 8
 NUM_STATS = 80
 OBS_STEP, OBS_RESET = 0, 1

@@ -11,7 +11,13 @@
 
 namespace wh {
 
-constexpr int BLOCK = 256;
+#ifndef WH_BLOCK
+#define WH_BLOCK 256
+#endif
+#ifndef WH_MIN_BLOCKS
+#define WH_MIN_BLOCKS 5
+#endif
+constexpr int BLOCK = WH_BLOCK;   // threads per block (tuning: -DWH_BLOCK / -DWH_MIN_BLOCKS)
 
 // ---------------------------------------------------------------------------------------------
 // kernels
@@ -44,7 +50,7 @@ struct StageMem {
 // Warehouse.step (+ optional in-kernel greedy solver, + optional observation build, + optional
 // auto-reset) — core.py:262-442, solvers.py:27-58
 template <int GC, int RC, bool GREEDY>
-__global__ void __launch_bounds__(BLOCK, 5) k_step(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(BLOCK, WH_MIN_BLOCKS) k_step(const __grid_constant__ KParams P) {
     __shared__ __align__(16) unsigned char smem[StageMem<GC, RC>::BYTES];
     const Group<GC> g(P.G);
     const Tile<GC> t(P, g);
