@@ -83,6 +83,9 @@ typedef struct wh_obs {
 
 #define WH_FLAG_AUTO_RESET 1   /* step: envs whose episode ends are reset in-kernel (native RNG) and
                                   their observation is the first one of the next episode */
+#define WH_FLAG_COMPACT_IO 2   /* wh_step: `actions` points to int8 [N,R] and `rewards` to uint8 [N,R]
+                                  (values 0/1/2) instead of int32 / float32 — 4x less PCIe traffic for
+                                  host-driven loops; semantics unchanged */
 
 /* stats vector (unsigned 64-bit counters, device memory, WH_NUM_STATS entries):
  * [0] episodes [1] return_sum [2] pickups [3] deliveries [4] expired [5..7] reserved
@@ -160,6 +163,8 @@ int wh_env_reset(wh_env *env);
  * obs_host (8 host pointers in wh_obs order, or NULL) additionally copies the observations out. */
 int wh_env_step_host(wh_env *env, const int32_t *actions, float *rewards, uint8_t *dones,
                      const wh_obs *obs_host);
+/* Same with WH_FLAG_COMPACT_IO dtypes on the wire: int8 actions in, uint8 rewards + uint8 dones out. */
+int wh_env_step_host_compact(wh_env *env, const int8_t *actions, uint8_t *rewards, uint8_t *dones);
 /* greedy-policy variant: the solver runs on device, nothing goes H2D; rewards/dones come back. */
 int wh_env_greedy_step_host(wh_env *env, float *rewards, uint8_t *dones);
 int wh_env_obs_ptrs(wh_env *env, wh_obs *out);      /* device pointers of the resident obs */

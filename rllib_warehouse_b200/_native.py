@@ -10,6 +10,7 @@ MAX_RACKS = 8
 NUM_STATS = 80
 OBS_STEP, OBS_RESET = 0, 1
 FLAG_AUTO_RESET = 1
+FLAG_COMPACT_IO = 2
 
 OBS_KEYS = (
     "num_agents", "self_position", "self_availability", "self_delivery_target",
@@ -21,7 +22,7 @@ STATE_KEYS = ("agent_pos", "agent_tgt", "pickup_tgt", "pickup_timer", "time", "n
 SYMBOLS = (
     "wh_version", "wh_error_string", "wh_num_pickup_points", "wh_num_delivery_points",
     "wh_reset", "wh_step", "wh_build_obs", "wh_build_obs_flat", "wh_greedy", "wh_greedy_step", "wh_stats_allreduce",
-    "wh_env_create", "wh_env_destroy", "wh_env_reset", "wh_env_step_host", "wh_env_greedy_step_host",
+    "wh_env_create", "wh_env_destroy", "wh_env_reset", "wh_env_step_host", "wh_env_step_host_compact", "wh_env_greedy_step_host",
     "wh_env_obs_ptrs", "wh_env_state_ptrs", "wh_env_stats_host", "wh_env_launch_count",
 )
 
@@ -74,6 +75,7 @@ def lib():
         L.wh_env_destroy.restype = None
         L.wh_env_reset.argtypes = [vp]
         L.wh_env_step_host.argtypes = [vp, vp, vp, vp, vp]
+        L.wh_env_step_host_compact.argtypes = [vp, vp, vp, vp]
         L.wh_env_greedy_step_host.argtypes = [vp, vp, vp]
         L.wh_env_obs_ptrs.argtypes = [vp, vp]
         L.wh_env_state_ptrs.argtypes = [vp, vp]

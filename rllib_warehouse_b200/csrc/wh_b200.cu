@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(BLOCK, WH_MIN_BLOCKS) k_step(const __grid_cons
         act = greedy_from_state<GC, RC>(P, g, R, env_id, s);
         if (P.actions_out && t.live && g.gl < R) P.actions_out[e * R + g.gl] = act;
     } else if (g.gl < R) {
-        act = P.actions[e * R + g.gl];
+        act = (P.flags & WH_FLAG_COMPACT_IO) ? (int)reinterpret_cast<const int8_t *>(P.actions)[e * R + g.gl]
+                                             : P.actions[e * R + g.gl];
         if (P.order) ord = P.order[e * R + g.gl];
     }
     s.time += 1;                                                               // core.py:267
@@ -76,7 +77,10 @@ __global__ void __launch_bounds__(BLOCK, WH_MIN_BLOCKS) k_step(const __grid_cons
 
     const bool done = s.time >= P.episode;                                     // core.py:438
     if (t.live) {
-        if (g.gl < R) P.rewards[e * R + g.gl] = so.reward;                      // core.py:435
+        if (g.gl < R) {                                                         // core.py:435
+            if (P.flags & WH_FLAG_COMPACT_IO) reinterpret_cast<uint8_t *>(P.rewards)[e * R + g.gl] = (uint8_t)so.reward;
+            else P.rewards[e * R + g.gl] = so.reward;
+        }
         if (g.gl == 0) P.dones[e] = done ? 1 : 0;
     }
     const bool auto_reset = (P.flags & WH_FLAG_AUTO_RESET) != 0;
@@ -556,7 +560,7 @@ int wh_env_reset(wh_env *E) {
 }
 
 static int env_step_impl(wh_env *E, const int32_t *actions, float *rewards, uint8_t *dones,
-                         const wh_obs *obs_host, bool greedy) {
+                         const wh_obs *obs_host, bool greedy, bool compact = false) {
     if (!E || !rewards || !dones || (!greedy && !actions)) return WH_E_ARG;
     CK(cudaSetDevice(E->device));
     const int64_t R = E->R;
@@ -572,14 +576,26 @@ static int env_step_impl(wh_env *E, const int32_t *actions, float *rewards, uint
                                 E->d_rewards + e0 * R, E->d_dones + e0, E->d_stats, &ob,
                                 WH_FLAG_AUTO_RESET, s);
         } else {
-            CK(cudaMemcpyAsync(E->d_actions + e0 * R, actions + e0 * R, n * R * 4, cudaMemcpyHostToDevice, s));
-            rc = wh_step(&E->cfg, &st, n, E->env_id0 + e0, E->seed, E->d_actions + e0 * R, nullptr, nullptr,
-                         nullptr, E->d_rewards + e0 * R, E->d_dones + e0, E->d_stats, &ob,
-                         WH_FLAG_AUTO_RESET, s);
+            if (compact) {
+                int8_t *da = reinterpret_cast<int8_t *>(E->d_actions) + e0 * R;
+                CK(cudaMemcpyAsync(da, reinterpret_cast<const int8_t *>(actions) + e0 * R, n * R, cudaMemcpyHostToDevice, s));
+                rc = wh_step(&E->cfg, &st, n, E->env_id0 + e0, E->seed, reinterpret_cast<const int32_t *>(da), nullptr,
+                             nullptr, nullptr, reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(E->d_rewards) + e0 * R),
+                             E->d_dones + e0, E->d_stats, &ob, WH_FLAG_AUTO_RESET | WH_FLAG_COMPACT_IO, s);
+            } else {
+                CK(cudaMemcpyAsync(E->d_actions + e0 * R, actions + e0 * R, n * R * 4, cudaMemcpyHostToDevice, s));
+                rc = wh_step(&E->cfg, &st, n, E->env_id0 + e0, E->seed, E->d_actions + e0 * R, nullptr, nullptr,
+                             nullptr, E->d_rewards + e0 * R, E->d_dones + e0, E->d_stats, &ob,
+                             WH_FLAG_AUTO_RESET, s);
+            }
         }
         E->launches += 1;
         if (rc) return rc;
-        CK(cudaMemcpyAsync(rewards + e0 * R, E->d_rewards + e0 * R, n * R * 4, cudaMemcpyDeviceToHost, s));
+        if (compact)
+            CK(cudaMemcpyAsync(reinterpret_cast<uint8_t *>(rewards) + e0 * R, reinterpret_cast<uint8_t *>(E->d_rewards) + e0 * R,
+                               n * R, cudaMemcpyDeviceToHost, s));
+        else
+            CK(cudaMemcpyAsync(rewards + e0 * R, E->d_rewards + e0 * R, n * R * 4, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(dones + e0, E->d_dones + e0, n, cudaMemcpyDeviceToHost, s));
         if (obs_host) {
             const wh_obs oh = offset_obs(*obs_host, e0, R);
@@ -600,6 +616,11 @@ static int env_step_impl(wh_env *E, const int32_t *actions, float *rewards, uint
 int wh_env_step_host(wh_env *E, const int32_t *actions, float *rewards, uint8_t *dones,
                      const wh_obs *obs_host) {
     return env_step_impl(E, actions, rewards, dones, obs_host, false);
+}
+
+int wh_env_step_host_compact(wh_env *E, const int8_t *actions, uint8_t *rewards, uint8_t *dones) {
+    return env_step_impl(E, reinterpret_cast<const int32_t *>(actions), reinterpret_cast<float *>(rewards), dones,
+                         nullptr, false, true);
 }
 
 int wh_env_greedy_step_host(wh_env *E, float *rewards, uint8_t *dones) {

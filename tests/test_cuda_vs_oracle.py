@@ -209,3 +209,46 @@ def test_flat_observations(size):
         env.reset()
         obs, _, _ = env.greedy_step()
         assert torch.equal(env.build_obs_flat(), env.flatten_obs(obs))
+
+
+@pytest.mark.parametrize("compact", [False, True])
+def test_host_buffer_layer(compact):
+    """Layer 2 of the C ABI (wh_env_*: host buffers, chunked copy/compute pipeline, both wire
+    formats) gives exactly what the device-pointer layer gives on the same seed and actions."""
+    import ctypes as C
+    from rllib_warehouse_b200 import MEDIUM, BatchedWarehouse
+    from rllib_warehouse_b200 import _native as nv
+    L = nv.lib()
+    n, R, seed, id0 = 5003, 9, 321, 1000
+    h = C.c_void_p()
+    cfg = nv.make_config(MEDIUM)
+    nv.check(L.wh_env_create(C.byref(cfg), n, 0, id0, seed, 3, C.byref(h)), "create")
+    nv.check(L.wh_env_reset(h), "reset")
+    twin = BatchedWarehouse(MEDIUM, n, seed=seed, env_id0=id0, auto_reset=True)
+    twin.reset()
+    rng = np.random.Generator(np.random.PCG64(3))
+    adt, rdt = (np.int8, np.uint8) if compact else (np.int32, np.float32)
+    rewards = torch.zeros((n, R), dtype=torch.uint8 if compact else torch.float32).pin_memory()
+    dones = torch.zeros(n, dtype=torch.uint8).pin_memory()
+    obs_host = {k: torch.zeros_like(v, device="cpu").pin_memory() for k, v in twin.obs.items()}
+    for t in range(205):
+        acts = torch.from_numpy(rng.integers(-1, 9, size=(n, R)).astype(adt)).pin_memory()
+        if compact:
+            nv.check(L.wh_env_step_host_compact(h, acts.data_ptr(), rewards.data_ptr(), dones.data_ptr()), "step")
+        else:
+            oh = nv.Obs(**{k: v.data_ptr() for k, v in obs_host.items()}) if t % 50 == 0 else None
+            nv.check(L.wh_env_step_host(h, acts.data_ptr(), rewards.data_ptr(), dones.data_ptr(),
+                                        C.byref(oh) if oh is not None else None), "step")
+        twin.step(acts.to(torch.int32))
+        assert torch.equal(rewards.to(torch.float32), twin.rewards.cpu()), t
+        assert torch.equal(dones, twin.dones.cpu()), t
+        if not compact and t % 50 == 0:
+            for k in obs_host:
+                assert torch.equal(obs_host[k], twin.obs[k].cpu()), (t, k)
+    stats = (C.c_ulonglong * nv.NUM_STATS)()
+    nv.check(L.wh_env_stats_host(h, stats), "stats")
+    assert list(stats) == twin.stats.cpu().tolist() and stats[0] == n
+    st = nv.State()
+    nv.check(L.wh_env_state_ptrs(h, C.byref(st)), "state ptrs")
+    assert st.agent_pos and L.wh_env_launch_count(h) == 1 + 205 * 3
+    L.wh_env_destroy(h)
