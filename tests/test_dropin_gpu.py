@@ -159,3 +159,28 @@ def test_vector_env_base_env_protocol(flat):
     o = venv.reset_tensors()
     o2, r2, d2 = venv.step_tensors(torch.zeros((n, twin.R), dtype=torch.int32, device="cuda"))
     assert r2.shape == (n, twin.R) and d2.shape == (n,)
+
+
+def test_batched_rollout_driver_with_torch_policy(tmp_path):
+    """scripts/rollout_batched.py: greedy policy and a TorchScript policy fed by the flat-obs kernel."""
+    import subprocess
+    import torch
+    R = 4
+
+    class Tiny(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.l = torch.nn.Linear(9 * R + 1, 9)
+
+        def forward(self, x):
+            return self.l(x / 12.0)
+
+    torch.manual_seed(0)
+    path = str(tmp_path / "policy.pt")
+    torch.jit.script(Tiny()).save(path)
+    script = os.path.join(ROOT, "scripts", "rollout_batched.py")
+    for extra in ([], ["--policy", path], ["--train-variant"]):
+        res = subprocess.run([sys.executable, script, "small", "--envs", "2048", "--episodes", "1", *extra],
+                             capture_output=True, text=True, timeout=300)
+        assert res.returncode == 0, res.stderr[-3000:]
+        assert "episodes: 2048" in res.stdout and "avg_agent_reward_all" in res.stdout, res.stdout
