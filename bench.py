@@ -5,8 +5,9 @@
     python bench.py --impl reference [--steps K] [--warmup W]      # CPU arm (oracle port, all host threads)
     torchrun --nproc-per-node N ... bench.py --gpus N ...          # one rank per GPU
 
-Workload (BASELINE.json configs[3]): WarehouseLarge, 16 agents, 262 144 envs in total, sharded
-contiguously over the GPUs (strong scaling; `--scaling weak` keeps 262 144 per GPU). A "step" is
+Workload (BASELINE.json configs[3]): WarehouseLarge, 16 agents, 262 144 envs per GPU, contiguous
+global env-id shards, no data-path collective (weak scaling: per-GPU work is fixed as N grows;
+`--scaling strong` splits a fixed total of 262 144 envs over the GPUs instead). A "step" is
 one `env.step` of every env: the fused move/collision/expiry/pickup/respawn/delivery kernel with
 the observation build, on int32 actions already resident in HBM (uniform-random; a pool of 200
 action tensors = one full episode of distinct actions, cycled). Observations (2.2 GB per step in total) are larger than L2, so no flush
@@ -25,6 +26,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# NCCL writes its banner / debug lines to stdout by default; stdout must carry exactly one JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 VARIANT_AGENTS = {"small": 4, "medium": 9, "large": 16}
 # compulsory I/O at API dtypes + narrow state read+write, per env-step (A = R)
@@ -39,8 +42,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--variant", default="large", choices=list(VARIANT_AGENTS))
-    ap.add_argument("--envs", type=int, default=262144, help="total envs (strong) / envs per GPU (weak)")
-    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--envs", type=int, default=262144, help="envs per GPU (weak, default) / total envs (strong)")
+    ap.add_argument("--scaling", default="weak", choices=["strong", "weak"])
     ap.add_argument("--policy", default="random", choices=["random", "greedy", "greedy_fused"])
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--e2e-chunks", type=int, default=8)
@@ -144,24 +147,27 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     rate = agent_steps / dt
     sample = (f"oracle/wh_oracle.c (C port of the reference step+obs; the Python reference cannot travel to "
-              f"the GPU box), {n} {args.variant} envs per step, random actions, {threads} pthreads")
+              f"the GPU box), bounded sample: {n} {args.variant} envs per step instead of the config's "
+              f"envs_total, random actions, {threads} pthreads")
     print(json.dumps({
         "impl": "reference", "metric": "agent_steps_per_sec", "value": rate, "unit": "agent-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": workload_config(args, n, 1),
+        "config": workload_config(args, max(1, args.gpus)),
         "cpu_baseline": {"value": rate, "unit": "agent-steps/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-def workload_config(args, envs_total, world):
+def workload_config(args, world):
+    per_gpu = args.envs if args.scaling == "weak" else args.envs // world
     return {
-        "workload": f"warehouse-{args.variant}-{args.envs}-envs", "variant": args.variant,
-        "agents_per_env": VARIANT_AGENTS[args.variant], "envs_total": envs_total,
-        "envs_per_gpu": envs_total // world, "policy": args.policy, "episode_steps": 200,
-        "l2": "obs written per step (>= 2 GB total) exceeds L2; no flush needed",
+        "workload": f"warehouse-{args.variant}-{args.envs}-envs-{'per-gpu' if args.scaling == 'weak' else 'total'}",
+        "variant": args.variant, "agents_per_env": VARIANT_AGENTS[args.variant],
+        "envs_total": per_gpu * world, "envs_per_gpu": per_gpu, "policy": args.policy, "episode_steps": 200,
+        "step": "one env.step of every env: fused move/collision/expiry/pickup/respawn/delivery + observation build",
+        "l2": "observations written per step (2.2 GB per GPU for large) exceed the 126 MB L2; no flush needed",
         "parallelism": f"env-sharded x{world}, no per-step communication",
     }
 
@@ -326,7 +332,7 @@ def run_b200(args):
         "metric": "agent_steps_per_sec", "value": value, "unit": "agent-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "int32",
-        "data": "synthetic", "config": workload_config(args, n_total, world),
+        "data": "synthetic", "config": workload_config(args, world),
         "roofline": roofline, "gpu_launches": gpu_launches, "launches_per_step": launches_per_step,
         "clocks": clocks.summary(),
     }
