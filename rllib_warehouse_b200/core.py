@@ -104,11 +104,34 @@ class Warehouse(MultiAgentEnv):
         return obs, rewards, dones, {str(i): {} for i in range(A)}
 
     def render(self, mode: str = "human", animate: bool = False) -> None:
-        """core.py:444-617 draws with gym's pyglet viewer, which is not available in this image;
-        the state needed for drawing is exposed through `render_state()`."""
-        raise NotImplementedError(
-            "rendering needs gym.envs.classic_control.rendering (pyglet); use render_state() to "
-            "obtain env-0 state on the host")
+        """core.py:444-617 draws env state with gym's pyglet viewer (agents, pickup racks, delivery
+        points, optional 10-frame interpolation). pyglet / a display are not available in this
+        image, so the bridge copies env-0 state to the host (`render_state`) and prints a text
+        frame with the same information: `.` floor, `p`/`P` idle/waiting pickup point, `d`/`D`
+        idle/targeted delivery point, digits = free agents, letters a.. = delivering agents.
+        `animate` is accepted for signature compatibility and ignored."""
+        if mode != "human":
+            raise NotImplementedError(f"render mode {mode!r}")                 # core.py:445-446
+        print(self.render_text())
+
+    def render_text(self) -> str:
+        st = self.render_state()
+        cfg, dim = self._config, self._config.area_dimension
+        grid = [["." for _ in range(dim)] for _ in range(dim)]
+        racks = cfg.pickup_racks_arrangement
+        cells = [(x + ox, y + oy) for x in racks for y in racks for ox, oy in ((-1, -1), (0, -1), (-1, 0), (0, 0))]
+        for p, (x, y) in enumerate(cells):                                     # core.py:171-175
+            grid[y][x] = "P" if st["pickup_point_targets"][p] > -1 else "p"
+        targeted = set(int(t) for t in st["agent_delivery_targets"] if t > -1)
+        targeted |= set(int(t) for t in st["pickup_point_targets"] if t > -1)
+        for d in range(cfg.num_delivery_points):                               # core.py:178-188
+            v, side = 2 + d // 4, d % 4
+            x, y = ((v, 0), (0, v), (v, dim - 1), (dim - 1, v))[side]
+            grid[y][x] = "D" if d in targeted else "d"
+        for i, ((x, y), t) in enumerate(zip(st["agent_positions"], st["agent_delivery_targets"])):
+            grid[int(y)][int(x)] = chr(ord("a") + i) if t > -1 else str(i % 10)
+        rows = ["".join(r) for r in reversed(grid)]                            # y = 0 at the bottom (core.py:14)
+        return f"t={st['episode_time']}\n" + "\n".join(rows)
 
     def render_state(self) -> Dict[str, np.ndarray]:
         st = self._batched.get_state()

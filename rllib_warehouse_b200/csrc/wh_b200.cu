@@ -25,13 +25,13 @@ constexpr int BLOCK = WH_BLOCK;   // threads per block (tuning: -DWH_BLOCK / -DW
 // Which environment a lane works for: warp w of the grid owns envs [w*epw, (w+1)*epw).
 template <int GC>
 struct Tile {
-    long long env, e;
+    env_t e;
     bool live;
     __device__ __forceinline__ Tile(const KParams &P, const Group<GC> &g) {
-        const long long warp = ((long long)blockIdx.x * BLOCK + threadIdx.x) >> 5;
-        env = warp * g.epw + g.gi;
-        live = !g.ghost && env < P.N;
-        e = (env < P.N) ? env : P.N - 1;   // dead lanes shadow a valid env so that loads stay in bounds
+        const uint32_t warp = blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5);
+        const uint32_t env = warp * (uint32_t)g.epw + (uint32_t)g.gi, n = (uint32_t)P.N;
+        live = !g.ghost && env < n;
+        e = (env < n) ? env : n - 1;   // dead lanes shadow a valid env so that loads stay in bounds
     }
 };
 
@@ -55,8 +55,8 @@ __global__ void __launch_bounds__(BLOCK, WH_MIN_BLOCKS) k_step(const __grid_cons
     const Group<GC> g(P.G);
     const Tile<GC> t(P, g);
     const int R = RC ? RC : P.R;
-    const long long e = t.e;
-    const uint32_t env_id = (uint32_t)(P.env_id0 + e);
+    const env_t e = t.e;
+    const uint32_t env_id = (uint32_t)P.env_id0 + e;
     EnvRegs s;
     load_env(P, g, e, R, s);
 
@@ -119,12 +119,12 @@ __global__ void __launch_bounds__(BLOCK) k_reset(const __grid_constant__ KParams
     const Group<GC> g(P.G);
     const Tile<GC> t(P, g);
     const int R = RC ? RC : P.R;
-    const long long e = t.e;
+    const env_t e = t.e;
     EnvRegs s;
     load_env(P, g, e, R, s);
     const bool doit = t.live && (!P.env_mask || P.env_mask[e]);
     const unsigned long long active =
-        do_reset(P, g, e, R, (uint32_t)(P.env_id0 + e), s, P.r_agent_pos != nullptr, doit);
+        do_reset(P, g, e, R, (uint32_t)P.env_id0 + e, s, P.r_agent_pos != nullptr, doit);
     if (doit) {
         store_env(P, g, e, R, s, true);
         if (g.gl == 0) reinterpret_cast<int4 *>(P.acc)[e] = make_int4(0, 0, 0, 0);
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(BLOCK) k_obs_flat(const __grid_constant__ KPar
     float *stage = nullptr;
     if (RC) stage = reinterpret_cast<float *>(smem + ((threadIdx.x >> 5) * EPW + (g.ghost ? 0 : g.gi)) * FlatStage<RC>::BYTES);
     build_obs_flat<GC, RC>(P, g, t.e, R, s, active, target_cell16(P, s.atgt), P.flavour, t.live,
-                           reinterpret_cast<float *>(P.rewards), stage);
+                           P.flat_out, stage);
 }
 
 // WarehouseRandomGreedySolver.compute_action on observation tensors — solvers.py:27-58.
@@ -316,6 +316,7 @@ static void launch_greedy(const KParams &K, cudaStream_t s) {
 
 static int launch(Kind kind, const KParams &K, const Shape &sh, void *stream) {
     if (K.N <= 0) return 0;
+    if ((unsigned long long)K.N * (K.R * K.R > 2 * K.P ? K.R * K.R : 2 * K.P) >= (1ull << 32)) return WH_E_CONFIG;   // 32-bit in-launch indexing: shard the batch
     cudaStream_t s = (cudaStream_t)stream;
     if (kind == K_GREEDY) {
         if (K.R == 4) launch_greedy<4, 1>(K, s);
@@ -416,7 +417,7 @@ int wh_build_obs_flat(const wh_config *cfg, const wh_state *st, int64_t n_envs, 
     if (int rc = fill_params(cfg, K, sh)) return rc;
     if (!state_ok(st) || !out || (flavour != WH_OBS_STEP && flavour != WH_OBS_RESET)) return WH_E_ARG;
     set_state(K, st);
-    K.rewards = out;   // the flat output travels in the `rewards` slot of the launch parameters
+    K.flat_out = out;
     K.N = n_envs; K.flavour = flavour;
     return launch(K_OBS_FLAT, K, sh, stream);
 }

@@ -20,6 +20,10 @@
 
 namespace wh {
 
+// Environment index inside one launch. 32-bit on purpose: every per-key element index (at most
+// e*R*R) then stays a single IMAD / IMAD.WIDE.U32; the launchers reject N*R*R >= 2^32.
+typedef uint32_t env_t;
+
 constexpr uint32_t FULL = 0xffffffffu;
 constexpr uint32_t ABSENT_MOVE = 0xffffffffu;
 constexpr uint32_t NO_CELL = 0xffff0000u;  // never equals a packed 16-bit cell
@@ -49,6 +53,7 @@ struct KParams {
     uint8_t *dones;
     unsigned long long *stats;
     int32_t *actions_out;
+    float *flat_out;    // RLlib-flattened observations [N,R,9R+1] (k_obs_flat)
     // reset replay
     const int8_t *r_agent_pos, *r_init_p, *r_init_t, *r_num_agents;
     const uint8_t *env_mask;
@@ -80,17 +85,20 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 
 __device__ __forceinline__ uint32_t bounded(uint32_t u, uint32_t n) { return __umulhi(u, n); }
 
-// index of the n-th (0-based, ascending) set bit (n < popc(mask)); WIDE = mask may use bits >= 32
-template <bool WIDE>
+// index of the n-th (0-based, ascending) set bit (n < popc(mask)); BITS = how many low bits of the
+// mask can be set (16 / 32 / 64) — the binary search skips the levels that cannot matter
+template <int BITS>
 __device__ __forceinline__ int nth_set64(unsigned long long m, int n) {
     uint32_t w = (uint32_t)m;
-    int pos = 0;
-    if (WIDE) {
-        const int c = __popc(w);
+    int pos = 0, c;
+    if (BITS > 32) {
+        c = __popc(w);
         if (n >= c) { n -= c; w = (uint32_t)(m >> 32); pos = 32; }
     }
-    int c = __popc(w & 0xFFFFu);
-    if (n >= c) { n -= c; w >>= 16; pos += 16; }
+    if (BITS > 16) {
+        c = __popc(w & 0xFFFFu);
+        if (n >= c) { n -= c; w >>= 16; pos += 16; }
+    }
     c = __popc(w & 0xFFu);
     if (n >= c) { n -= c; w >>= 8; pos += 8; }
     c = __popc(w & 0xFu);
@@ -145,6 +153,7 @@ struct Group {
     uint32_t gmask;   // this group's lanes
     bool ghost;       // one of the 32 mod G left-over lanes: computes along, owns nothing
     static constexpr bool WIDE = (GC == 0) || (4 * GC > 32);   // pickup masks may need > 32 bits
+    static constexpr int PBITS = (GC == 0) ? 64 : (4 * GC <= 16 ? 16 : (4 * GC <= 32 ? 32 : 64));   // pickup-mask width
     static constexpr bool POW2 = GC != 0 && (GC & (GC - 1)) == 0;
     __device__ __forceinline__ explicit Group(int g_runtime) {
         G = GC ? GC : g_runtime;
@@ -233,7 +242,7 @@ struct EnvRegs {
 };
 
 template <int GC>
-__device__ __forceinline__ void load_env(const KParams &P, const Group<GC> &g, long long e, int R, EnvRegs &s) {
+__device__ __forceinline__ void load_env(const KParams &P, const Group<GC> &g, env_t e, int R, EnvRegs &s) {
     s.time = P.time[e];
     s.A = P.num_agents[e];
     s.ep = P.episode_ctr[e];
@@ -254,7 +263,7 @@ __device__ __forceinline__ void load_env(const KParams &P, const Group<GC> &g, l
 }
 
 template <int GC>
-__device__ __forceinline__ void store_env(const KParams &P, const Group<GC> &g, long long e, int R,
+__device__ __forceinline__ void store_env(const KParams &P, const Group<GC> &g, env_t e, int R,
                                           const EnvRegs &s, bool store_meta) {
     if (g.gl < R) {
         reinterpret_cast<uint16_t *>(P.agent_pos)[e * R + g.gl] = (uint16_t)s.pos16;
@@ -290,8 +299,8 @@ __device__ __forceinline__ unsigned long long active_mask(const Group<GC> &g, ui
 //            occ[c] is True  <=>  some lane has mark == c.  A successful move from p clears the
 //            mark of EVERY agent standing on p (core.py:290 clears the bit even if a co-located
 //            agent remains) and sets the mover's mark to its new cell (core.py:291).
-//   f0/f1/f2 : the up-to-three moves this agent's successful move forbids (core.py:294-297): the
-//            reverse move and, for a diagonal, the two crossing moves; armed once it has moved.
+//   rev/ca/cb : the up-to-three moves this agent's successful move forbids (core.py:294-297): the
+//            reverse move and, for a diagonal, the two crossing moves; armed (`moved`) on success.
 // One ballot per processed agent answers "is the target marked, or is this move forbidden?".
 template <int GC, int RC>
 __device__ __forceinline__ void do_moves(const KParams &P, const Group<GC> &g, int R, int A,
@@ -314,9 +323,7 @@ __device__ __forceinline__ void do_moves(const KParams &P, const Group<GC> &g, i
         }
     }
     uint32_t mark = (g.gl < A) ? pos16 : NO_CELL;   // core.py:276: every agent marks its cell
-    // armed forbidden moves; 0xFFFF0000-style values can never equal a real move (from-cell 0xFFFF
-    // never moves), and an ABSENT move is rejected below whatever `hit` says
-    uint32_t f0 = 0xFFFFFFFEu, f1 = 0xFFFFFFFEu, f2 = 0xFFFFFFFEu;
+    bool moved = false;   // arms rev / ca / cb (an ABSENT move is rejected below whatever `hit` says)
     int n_order = R;
     if (have_order) {  // entries after the first -1 are ignored
         const uint32_t neg = g.ballot(g.gl < R && ord < 0);
@@ -331,22 +338,23 @@ __device__ __forceinline__ void do_moves(const KParams &P, const Group<GC> &g, i
             uint32_t mm = g.shfl(m, cur < 0 ? 0 : cur);
             if (cur < 0) mm = ABSENT_MOVE;
             const uint32_t c = mm >> 16, from = mm & 0xFFFFu;
-            const bool hit = (mark == c) | (f0 == mm) | (f1 == mm) | (f2 == mm);
+            const bool hit = (mark == c) | (moved & ((rev == mm) | (ca == mm) | (cb == mm)));
             const bool ok = (g.ballot(hit) == 0u) && (mm != ABSENT_MOVE);      // core.py:289
             if (ok && mark == from) mark = NO_CELL;                            // core.py:290
-            if (ok && g.gl == cur) { mark = c; pos16 = c; f0 = rev; f1 = ca; f2 = cb; }   // core.py:291-300
+            if (ok && g.gl == cur) { mark = c; moved = true; }                 // core.py:291-297
         }
     } else {
 #pragma unroll
         for (int t = 0; t < RR; ++t) {                                         // ascending agent ids
             const uint32_t mm = g.shfl(m, t);
             const uint32_t c = mm >> 16, from = mm & 0xFFFFu;
-            const bool hit = (mark == c) | (f0 == mm) | (f1 == mm) | (f2 == mm);
+            const bool hit = (mark == c) | (moved & ((rev == mm) | (ca == mm) | (cb == mm)));
             const bool ok = (g.ballot(hit) == 0u) && (mm != ABSENT_MOVE);      // core.py:289
             if (ok && mark == from) mark = NO_CELL;                            // core.py:290
-            if (ok && g.gl == t) { mark = c; pos16 = c; f0 = rev; f1 = ca; f2 = cb; }     // core.py:291-300
+            if (ok && g.gl == t) { mark = c; moved = true; }                   // core.py:291-297
         }
     }
+    if (moved) pos16 = m >> 16;                                                // core.py:299-300
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -360,9 +368,8 @@ struct StepOut {
 };
 
 template <int GC>
-__device__ __forceinline__ StepOut do_world(const KParams &P, const Group<GC> &g, long long e, int R,
+__device__ __forceinline__ StepOut do_world(const KParams &P, const Group<GC> &g, env_t e, int R,
                                             uint32_t env_id, EnvRegs &s, bool replay) {
-    constexpr bool WIDE = Group<GC>::WIDE;
     StepOut o;
     // ---- core.py:303-306 expiry (before pickup detection) ----
     int nexp = 0;
@@ -416,8 +423,8 @@ __device__ __forceinline__ StepOut do_world(const KParams &P, const Group<GC> &g
             } else {
                 const uint32_t a = g.shfl(up, i), b = g.shfl(ut, i);
                 const int ni = n_inact - i, di = P.D - i;
-                p = nth_set64<WIDE>(inactive, (int)bounded(a, (uint32_t)(ni > 0 ? ni : 1)));
-                d = nth_set64<true>(avail_d, (int)bounded(b, (uint32_t)(di > 0 ? di : 1)));
+                p = nth_set64<Group<GC>::PBITS>(inactive, (int)bounded(a, (uint32_t)(ni > 0 ? ni : 1)));
+                d = nth_set64<64>(avail_d, (int)bounded(b, (uint32_t)(di > 0 ? di : 1)));
             }
             if (i < k && p >= 0) {
                 inactive &= ~(1ull << p);
@@ -467,10 +474,9 @@ struct ObsStage {
 };
 
 template <int GC, int RC>
-__device__ __forceinline__ void build_obs(const KParams &P, const Group<GC> &g, long long e, int R,
+__device__ __forceinline__ void build_obs(const KParams &P, const Group<GC> &g, env_t e, int R,
                                           const EnvRegs &s, unsigned long long active, uint32_t tpos16,
                                           int flavour, bool live, unsigned char *stage) {
-    constexpr bool WIDE = Group<GC>::WIDE;
     const int null_pos = P.null_pos;
     const uint32_t null16 = (uint32_t)null_pos | ((uint32_t)null_pos << 8);
     const bool real = g.gl < s.A;
@@ -489,7 +495,7 @@ __device__ __forceinline__ void build_obs(const KParams &P, const Group<GC> &g, 
 
     // core.py:409-418 request list: active pickup points in ascending index, [px,py,dx,dy]
     const bool have = g.gl < R && g.gl < __popcll(active);
-    const int p = nth_set64<WIDE>(active, have ? g.gl : 0) & 63;
+    const int p = nth_set64<Group<GC>::PBITS>(active, have ? g.gl : 0) & 63;
     const uint32_t w4 = g.shfl(s.pt4, p >> 2);
     int4 rq = make_int4(null_pos, null_pos, null_pos, null_pos);  // only if < R active (unreachable)
     if (have) {
@@ -499,7 +505,7 @@ __device__ __forceinline__ void build_obs(const KParams &P, const Group<GC> &g, 
     }
 
     const wh_obs &o = P.obs;
-    const long long row0 = e * R;
+    const uint32_t row0 = e * (uint32_t)R;
     if (live && g.gl < R) {
         o.num_agents[row0 + g.gl] = s.A;
         reinterpret_cast<int2 *>(o.self_position)[row0 + g.gl] = my_p;
@@ -603,10 +609,9 @@ struct FlatStage {
 };
 
 template <int GC, int RC>
-__device__ __forceinline__ void build_obs_flat(const KParams &P, const Group<GC> &g, long long e, int R,
+__device__ __forceinline__ void build_obs_flat(const KParams &P, const Group<GC> &g, env_t e, int R,
                                                const EnvRegs &s, unsigned long long active, uint32_t tpos16,
                                                int flavour, bool live, float *out, float *stage) {
-    constexpr bool WIDE = Group<GC>::WIDE;
     const int null_pos = P.null_pos;
     const uint32_t null16 = (uint32_t)null_pos | ((uint32_t)null_pos << 8);
     const bool real = g.gl < s.A;
@@ -618,7 +623,7 @@ __device__ __forceinline__ void build_obs_flat(const KParams &P, const Group<GC>
                           (((tpos >> 8) & 0x7Fu) << 21) | (avail << 28);
     const uint32_t next = g.shfl_down1(mine);
     const bool have = g.gl < R && g.gl < __popcll(active);
-    const int p = nth_set64<WIDE>(active, have ? g.gl : 0) & 63;
+    const int p = nth_set64<Group<GC>::PBITS>(active, have ? g.gl : 0) & 63;
     const uint32_t w4 = g.shfl(s.pt4, p >> 2);
     float4 rq = make_float4((float)null_pos, (float)null_pos, (float)null_pos, (float)null_pos);
     if (have) {
@@ -655,7 +660,7 @@ __device__ __forceinline__ void build_obs_flat(const KParams &P, const Group<GC>
             dst[9 * R - 1] = px(mine); dst[9 * R] = py(mine);
         }
     };
-    float *env_out = out + e * (long long)R * F;
+    float *env_out = out + (long long)e * R * F;
     if constexpr (RC != 0) {
         using St = FlatStage<RC>;
 #pragma unroll
@@ -691,10 +696,9 @@ __device__ __forceinline__ uint32_t target_cell16(const KParams &P, int atgt) {
 // reset — core.py:167-221, variants.py:69-74
 // ---------------------------------------------------------------------------------------------
 template <int GC>
-__device__ __forceinline__ unsigned long long do_reset(const KParams &P, const Group<GC> &g, long long e,
+__device__ __forceinline__ unsigned long long do_reset(const KParams &P, const Group<GC> &g, env_t e,
                                                        int R, uint32_t env_id, EnvRegs &s, bool replay,
                                                        bool doit) {
-    constexpr bool WIDE = Group<GC>::WIDE;
     // `doit` is uniform within the group; groups that skip still take part in warp-wide votes
     EnvRegs n = s;
     n.ep = s.ep + 1;
@@ -742,8 +746,8 @@ __device__ __forceinline__ unsigned long long do_reset(const KParams &P, const G
             d = (int)g.shfl((uint32_t)st_, i);
         } else {
             const uint32_t a = g.shfl(u0, i), b = g.shfl(u1, i);
-            p = nth_set64<WIDE>(inactive, (int)bounded(a, (uint32_t)(P.P - i)));
-            d = nth_set64<true>(avail_d, (int)bounded(b, (uint32_t)(P.D - i)));
+            p = nth_set64<Group<GC>::PBITS>(inactive, (int)bounded(a, (uint32_t)(P.P - i)));
+            d = nth_set64<64>(avail_d, (int)bounded(b, (uint32_t)(P.D - i)));
         }
         if (p >= 0) {
             inactive &= ~(1ull << p);
@@ -772,13 +776,12 @@ __device__ __forceinline__ unsigned long long do_reset(const KParams &P, const G
 template <int GC, int RC>
 __device__ __forceinline__ int greedy_from_state(const KParams &P, const Group<GC> &g, int R,
                                                  uint32_t env_id, const EnvRegs &s) {
-    constexpr bool WIDE = Group<GC>::WIDE;
     const unsigned long long active = active_mask(g, s.pt4);
     const int px = s.pos16 & 0xFF, py = s.pos16 >> 8;
     // lane r takes the r-th active pickup point's cell
     const int nact = __popcll(active);
     uint32_t cell = (uint32_t)P.null_pos | ((uint32_t)P.null_pos << 8);
-    if (g.gl < nact && g.gl < R) cell = pickup_cell16(P, nth_set64<WIDE>(active, g.gl));
+    if (g.gl < nact && g.gl < R) cell = pickup_cell16(P, nth_set64<Group<GC>::PBITS>(active, g.gl));
     int best = 1 << 30;
     uint32_t bcell = 0;
     const int RR = RC ? RC : R;
