@@ -115,6 +115,13 @@ int wh_step(const wh_config *cfg, const wh_state *st, int64_t n_envs, int64_t en
             float *rewards, uint8_t *dones, unsigned long long *stats,
             const wh_obs *obs, int flags, void *stream);
 
+/* wh_step with the observations emitted directly in RLlib's flattened float32 layout
+ * (see wh_build_obs_flat) by the same kernel — the path a vectorised RLlib sampler consumes.
+ * flat_obs [N, R, 9R+1] float32. With WH_FLAG_AUTO_RESET finished envs get their reset observation. */
+int wh_step_flat(const wh_config *cfg, const wh_state *st, int64_t n_envs, int64_t env_id0, uint64_t seed,
+                 const int32_t *actions, const int32_t *order, float *rewards, uint8_t *dones,
+                 unsigned long long *stats, float *flat_obs, int flags, void *stream);
+
 /* Observation build alone — flavour WH_OBS_STEP (core.py:371-432) or WH_OBS_RESET (core.py:224-260). */
 int wh_build_obs(const wh_config *cfg, const wh_state *st, int64_t n_envs, int flavour,
                  const wh_obs *obs, void *stream);

@@ -130,6 +130,26 @@ class BatchedWarehouse:
         self.launches += 1
         return self.obs, self.rewards, self.dones
 
+    def step_flat(self, actions, order=None, out=None):
+        """`step` whose observations are RLlib-flattened float32 [N, R, 9R+1], written by the step
+        kernel itself (no dict-keyed tensors are produced)."""
+        dev, N, R = self.device, self.N, self.R
+        actions = _dev_tensor(actions, torch.int32, dev, (N, R))
+        order = _dev_tensor(order, torch.int32, dev, (N, R))
+        if out is None:
+            if getattr(self, "_flat", None) is None:
+                self._flat = torch.empty((N, R, 9 * R + 1), dtype=torch.float32, device=dev)
+            out = self._flat
+        flags = nv.FLAG_AUTO_RESET if self.auto_reset else 0
+        with torch.cuda.device(dev):
+            rc = self.lib.wh_step_flat(C.byref(self._cfg), C.byref(self._st), N, self.env_id0, self.seed,
+                                       _ptr(actions), _ptr(order), self.rewards.data_ptr(),
+                                       self.dones.data_ptr(), self.stats.data_ptr(), out.data_ptr(),
+                                       flags, self._stream())
+        nv.check(rc, "wh_step_flat")
+        self.launches += 1
+        return out, self.rewards, self.dones
+
     def greedy_step(self, random_action_prob=0.0, solver_seed=0, with_obs=True, want_actions=True):
         """One run.py:42-62 loop iteration for all envs in a single kernel: greedy solver
         (solvers.py:27-58) evaluated from the resident state, then step + observation build."""

@@ -36,22 +36,24 @@ struct Tile {
 };
 
 // per-block staging for the observation build: one ObsStage per environment slot of the block
-template <int GC, int RC>
+template <int GC, int RC, bool FLAT = false>
 struct StageMem {
     static constexpr int EPW = GC ? 32 / GC : 1;
-    static constexpr int BYTES = RC ? (BLOCK / 32) * EPW * ObsStage<RC>::BYTES : 16;
+    // a slot serves one observation layout: dict keys (ObsStage) or RLlib-flattened (FlatStage)
+    static constexpr int SLOT = FLAT ? FlatStage<RC>::BYTES : ObsStage<RC>::BYTES;
+    static constexpr int BYTES = RC ? (BLOCK / 32) * EPW * SLOT : 16;
     __device__ static __forceinline__ unsigned char *mine(unsigned char *base, const Group<GC> &g) {
         if (RC == 0) return nullptr;
         const int slot = (threadIdx.x >> 5) * EPW + (g.ghost ? 0 : g.gi);
-        return base + slot * ObsStage<RC>::BYTES;
+        return base + slot * SLOT;
     }
 };
 
 // Warehouse.step (+ optional in-kernel greedy solver, + optional observation build, + optional
 // auto-reset) — core.py:262-442, solvers.py:27-58
-template <int GC, int RC, bool GREEDY>
+template <int GC, int RC, bool GREEDY, bool FLAT>
 __global__ void __launch_bounds__(BLOCK, WH_MIN_BLOCKS) k_step(const __grid_constant__ KParams P) {
-    __shared__ __align__(16) unsigned char smem[StageMem<GC, RC>::BYTES];
+    __shared__ __align__(16) unsigned char smem[StageMem<GC, RC, FLAT>::BYTES];
     const Group<GC> g(P.G);
     const Tile<GC> t(P, g);
     const int R = RC ? RC : P.R;
@@ -109,7 +111,11 @@ __global__ void __launch_bounds__(BLOCK, WH_MIN_BLOCKS) k_step(const __grid_cons
         meta = true;
     }
     if (t.live) store_env(P, g, e, R, s, meta);
-    if (P.obs.requests) build_obs<GC, RC>(P, g, e, R, s, active, tpos16, flavour, t.live, StageMem<GC, RC>::mine(smem, g));
+    if (FLAT)   // RLlib-flattened float32 layout instead of the dict keys (separate instantiation)
+        build_obs_flat<GC, RC>(P, g, e, R, s, active, tpos16, flavour, t.live, P.flat_out,
+                               reinterpret_cast<float *>(StageMem<GC, RC, true>::mine(smem, g)));
+    else if (P.obs.requests)
+        build_obs<GC, RC>(P, g, e, R, s, active, tpos16, flavour, t.live, StageMem<GC, RC>::mine(smem, g));
 }
 
 // Warehouse.reset — core.py:167-260
@@ -148,18 +154,15 @@ __global__ void __launch_bounds__(BLOCK) k_obs(const __grid_constant__ KParams P
 // RLlib-flattened float32 observations from the resident state
 template <int GC, int RC>
 __global__ void __launch_bounds__(BLOCK) k_obs_flat(const __grid_constant__ KParams P) {
-    constexpr int EPW = GC ? 32 / GC : 1;
-    __shared__ __align__(16) unsigned char smem[RC ? (BLOCK / 32) * EPW * FlatStage<RC>::BYTES : 16];
+    __shared__ __align__(16) unsigned char smem[StageMem<GC, RC, true>::BYTES];
     const Group<GC> g(P.G);
     const Tile<GC> t(P, g);
     const int R = RC ? RC : P.R;
     EnvRegs s;
     load_env(P, g, t.e, R, s);
     const unsigned long long active = active_mask(g, s.pt4);
-    float *stage = nullptr;
-    if (RC) stage = reinterpret_cast<float *>(smem + ((threadIdx.x >> 5) * EPW + (g.ghost ? 0 : g.gi)) * FlatStage<RC>::BYTES);
     build_obs_flat<GC, RC>(P, g, t.e, R, s, active, target_cell16(P, s.atgt), P.flavour, t.live,
-                           P.flat_out, stage);
+                           P.flat_out, reinterpret_cast<float *>(StageMem<GC, RC, true>::mine(smem, g)));
 }
 
 // WarehouseRandomGreedySolver.compute_action on observation tensors — solvers.py:27-58.
@@ -290,7 +293,7 @@ static bool obs_ok(const wh_obs *o) {
            o->other_positions && o->other_availabilities && o->other_delivery_targets && o->requests;
 }
 
-enum Kind { K_STEP, K_GSTEP, K_RESET, K_OBS, K_OBS_FLAT, K_GREEDY };
+enum Kind { K_STEP, K_GSTEP, K_STEP_FLAT, K_RESET, K_OBS, K_OBS_FLAT, K_GREEDY };
 
 template <int GC, int RC>
 static void launch_kind(Kind kind, const KParams &K, cudaStream_t s) {
@@ -298,8 +301,9 @@ static void launch_kind(Kind kind, const KParams &K, cudaStream_t s) {
     const long long epw = 32 / G, warps = (K.N + epw - 1) / epw;
     const unsigned grid = (unsigned)((warps * 32 + BLOCK - 1) / BLOCK);
     switch (kind) {
-    case K_STEP: k_step<GC, RC, false><<<grid, BLOCK, 0, s>>>(K); break;
-    case K_GSTEP: k_step<GC, RC, true><<<grid, BLOCK, 0, s>>>(K); break;
+    case K_STEP: k_step<GC, RC, false, false><<<grid, BLOCK, 0, s>>>(K); break;
+    case K_GSTEP: k_step<GC, RC, true, false><<<grid, BLOCK, 0, s>>>(K); break;
+    case K_STEP_FLAT: k_step<GC, RC, false, true><<<grid, BLOCK, 0, s>>>(K); break;
     case K_RESET: k_reset<GC, RC><<<grid, BLOCK, 0, s>>>(K); break;
     case K_OBS: k_obs<GC, RC><<<grid, BLOCK, 0, s>>>(K); break;
     case K_OBS_FLAT: k_obs_flat<GC, RC><<<grid, BLOCK, 0, s>>>(K); break;
@@ -384,6 +388,20 @@ int wh_step(const wh_config *cfg, const wh_state *st, int64_t n_envs, int64_t en
     K.actions = actions; K.order = order; K.spawn_p = spawn_pickups; K.spawn_t = spawn_targets;
     K.rewards = rewards; K.dones = dones; K.stats = stats; K.flags = flags;
     return launch(K_STEP, K, sh, stream);
+}
+
+int wh_step_flat(const wh_config *cfg, const wh_state *st, int64_t n_envs, int64_t env_id0, uint64_t seed,
+                 const int32_t *actions, const int32_t *order, float *rewards, uint8_t *dones,
+                 unsigned long long *stats, float *flat_obs, int flags, void *stream) {
+    KParams K; Shape sh;
+    if (int rc = fill_params(cfg, K, sh)) return rc;
+    if (!state_ok(st) || !actions || !rewards || !dones || !flat_obs) return WH_E_ARG;
+    set_state(K, st);
+    K.flat_out = flat_obs;
+    K.N = n_envs; K.env_id0 = env_id0; K.seed = seed;
+    K.actions = actions; K.order = order;
+    K.rewards = rewards; K.dones = dones; K.stats = stats; K.flags = flags;
+    return launch(K_STEP_FLAT, K, sh, stream);
 }
 
 int wh_greedy_step(const wh_config *cfg, const wh_state *st, int64_t n_envs, int64_t env_id0,

@@ -53,8 +53,7 @@ class WarehouseVectorEnv(BaseEnv):
     def step_tensors(self, actions: torch.Tensor):
         """actions [N,R] integer tensor (-1 = no action). Returns (obs, rewards[N,R], dones[N])."""
         if self.flat_obs:
-            _, rew, dones = self.env.step(actions, with_obs=False)
-            return self.env.build_obs_flat(nv.OBS_STEP), rew, dones
+            return self.env.step_flat(actions)       # one kernel: step + flattened observations
         return self.env.step(actions)
 
     # ---- BaseEnv protocol ----------------------------------------------------------------------

@@ -252,3 +252,26 @@ def test_host_buffer_layer(compact):
     nv.check(L.wh_env_state_ptrs(h, C.byref(st)), "state ptrs")
     assert st.agent_pos and L.wh_env_launch_count(h) == 1 + 205 * 3
     L.wh_env_destroy(h)
+
+
+@pytest.mark.parametrize("size", list(SIZES))
+def test_step_with_fused_flat_observations(size):
+    """wh_step_flat (step kernel emitting RLlib-flattened float32 obs itself) == wh_step + flatten,
+    across an auto-reset boundary (reset-flavour observations for finished envs)."""
+    from rllib_warehouse_b200 import VARIANTS, BatchedWarehouse
+    n = 777
+    cfg = VARIANTS[size].replace(random_num_agents=True, episode_duration=12)
+    a = BatchedWarehouse(cfg, n, seed=9, auto_reset=True)
+    b = BatchedWarehouse(cfg, n, seed=9, auto_reset=True)
+    a.reset(); b.reset()
+    rng = np.random.Generator(np.random.PCG64(2))
+    for t in range(30):
+        acts = rng.integers(-1, 9, size=(n, a.R)).astype(np.int32)
+        order = np.stack([rng.permutation(a.R) for _ in range(n)]).astype(np.int32) if t % 4 == 0 else None
+        obs, rew, dones = a.step(acts, order=order)
+        flat, rew2, dones2 = b.step_flat(acts, order=order)
+        assert torch.equal(flat, a.flatten_obs(obs)), t
+        assert torch.equal(rew, rew2) and torch.equal(dones, dones2)
+    for k in a.state:
+        assert torch.equal(a.state[k], b.state[k]), k
+    assert torch.equal(a.stats, b.stats) and int(a.stats[0]) == 2 * n
