@@ -451,6 +451,19 @@ def extras(args, dev, peak):
         }
         del env
         torch.cuda.empty_cache()
+    # BASELINE configs[1] shape (Small, 4 096 envs): launch-bound eagerly, so also as a CUDA graph
+    from rllib_warehouse_b200 import StepGraph
+    env = BatchedWarehouse(VARIANTS["small"], 4096, device=dev, seed=args.seed + 2, auto_reset=True)
+    env.reset()
+    ms_eager = _time_steps(lambda i: env.greedy_step(want_actions=False), 400, 20)
+    graph = StepGraph(env, steps=50, policy="greedy")
+    ms_graph = _time_steps(lambda i: graph.replay(), 20, 3) / 50
+    res["configs1_small_4096"] = {
+        "fused_greedy_step_eager": {"ms": ms_eager, "agent_steps_per_sec": 4096 * 4 / (ms_eager * 1e-3)},
+        "fused_greedy_step_cuda_graph": {"ms": ms_graph, "agent_steps_per_sec": 4096 * 4 / (ms_graph * 1e-3),
+                                         "frac": ALG_BYTES_PER_ENV_STEP["small"] * 4096 / ms_graph / 1e6 / peak,
+                                         "note": "50 steps per graph replay; the whole working set fits in L2"},
+    }
     return res
 
 

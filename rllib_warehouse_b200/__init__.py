@@ -6,7 +6,7 @@ Reference-compatible surface: `Warehouse`, `WarehouseSmall/Medium/Large`, `Wareh
 Batched surface: `BatchedWarehouse`, `BatchedGreedySolver`.
 """
 from .config import LARGE, MEDIUM, SMALL, VARIANTS, WarehouseConfig
-from .batched import BatchedWarehouse
+from .batched import BatchedWarehouse, StepGraph
 from .core import Warehouse
 from .variants import (WarehouseLarge, WarehouseLargeTrain, WarehouseMedium, WarehouseMediumTrain,
                        WarehouseSmall, WarehouseSmallTrain)
@@ -17,6 +17,6 @@ __all__ = [
     "Warehouse", "WarehouseSmall", "WarehouseMedium", "WarehouseLarge",
     "WarehouseSmallTrain", "WarehouseMediumTrain", "WarehouseLargeTrain",
     "WarehouseConfig", "SMALL", "MEDIUM", "LARGE", "VARIANTS",
-    "BatchedWarehouse", "WarehouseVectorEnv", "BatchedGreedySolver", "WarehouseRandomGreedySolver", "WarehouseSolver",
+    "BatchedWarehouse", "StepGraph", "WarehouseVectorEnv", "BatchedGreedySolver", "WarehouseRandomGreedySolver", "WarehouseSolver",
 ]
 name = "rllib_warehouse_b200"

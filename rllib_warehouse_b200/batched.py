@@ -254,3 +254,46 @@ class BatchedWarehouse:
         if out["episodes"]:
             out["avg_agent_reward_all"] = tot_avg_num / out["episodes"]
         return out
+
+
+class StepGraph:
+    """CUDA-graph capture of `steps` consecutive environment steps for launch-bound batch sizes
+    (e.g. BASELINE configs[1]: 4 096 Small envs, where one step kernel takes ~3 us but a Python
+    launch ~10 us). policy="greedy": the fused solver+step kernel, no inputs. policy="actions":
+    every captured step reads `self.actions` ([steps, N, R] int32), which the caller overwrites in
+    place before `replay()`. Observations / rewards / dones land in the env's resident tensors
+    (the values after the LAST captured step; per-step rewards are accumulated in
+    `self.reward_sum` [N, R])."""
+
+    def __init__(self, env: BatchedWarehouse, steps: int = 1, policy: str = "greedy", with_obs: bool = True,
+                 random_action_prob: float = 0.0, solver_seed: int = 0):
+        assert policy in ("greedy", "actions")
+        self.env, self.steps, self.policy = env, int(steps), policy
+        dev = env.device
+        self.actions = torch.zeros((self.steps, env.N, env.R), dtype=torch.int32, device=dev)
+        self.reward_sum = torch.zeros((env.N, env.R), dtype=torch.float32, device=dev)
+
+        def body():
+            self.reward_sum.zero_()
+            for t in range(self.steps):
+                if policy == "greedy":
+                    env.greedy_step(random_action_prob, solver_seed, with_obs=with_obs, want_actions=False)
+                else:
+                    env.step(self.actions[t], with_obs=with_obs)
+                self.reward_sum.add_(env.rewards)
+
+        # capture never executes, so no warm-up run is needed (and it would advance the env)
+        self.graph = torch.cuda.CUDAGraph()
+        launches0 = env.launches
+        with torch.cuda.device(dev):
+            stream = torch.cuda.Stream(device=dev)
+            stream.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.graph(self.graph, stream=stream):
+                body()
+        self.launches_per_replay = env.launches - launches0
+        env.launches = launches0
+
+    def replay(self):
+        self.graph.replay()
+        self.env.launches += self.launches_per_replay
+        return self.env.obs, self.env.rewards, self.env.dones
