@@ -14,8 +14,20 @@ namespace wh {
 #ifndef WH_BLOCK
 #define WH_BLOCK 256
 #endif
+// Resident blocks per SM the register allocator must allow (measured optimum per variant,
+// profiles/README.md): Large is fastest with FEWER, fatter warps (72 registers, 3 blocks = 24 warps:
+// fewer concurrent write streams), Medium with 5, Small (issue-bound) with 6.
 #ifndef WH_MIN_BLOCKS
 #define WH_MIN_BLOCKS 5
+#endif
+#ifndef WH_MIN_BLOCKS_LARGE
+#define WH_MIN_BLOCKS_LARGE 3
+#endif
+#ifndef WH_MIN_BLOCKS_MEDIUM
+#define WH_MIN_BLOCKS_MEDIUM 5
+#endif
+#ifndef WH_MIN_BLOCKS_SMALL
+#define WH_MIN_BLOCKS_SMALL 6
 #endif
 constexpr int BLOCK = WH_BLOCK;   // threads per block (tuning: -DWH_BLOCK / -DWH_MIN_BLOCKS)
 
@@ -52,7 +64,7 @@ struct StageMem {
 // Warehouse.step (+ optional in-kernel greedy solver, + optional observation build, + optional
 // auto-reset) — core.py:262-442, solvers.py:27-58
 template <int GC, int RC, bool GREEDY, bool FLAT>
-__global__ void __launch_bounds__(BLOCK, WH_MIN_BLOCKS) k_step(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(BLOCK, (RC == 16 ? WH_MIN_BLOCKS_LARGE : RC == 9 ? WH_MIN_BLOCKS_MEDIUM : RC == 4 ? WH_MIN_BLOCKS_SMALL : WH_MIN_BLOCKS)) k_step(const __grid_constant__ KParams P) {
     __shared__ __align__(16) unsigned char smem[StageMem<GC, RC, FLAT>::BYTES];
     const Group<GC> g(P.G);
     const Tile<GC> t(P, g);

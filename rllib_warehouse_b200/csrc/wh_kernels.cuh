@@ -18,11 +18,22 @@
 
 #include "../../include/wh_b200.h"
 
+// Observation stores are written once and never re-read by these kernels. Measured on B200
+// (profiles/README.md): for the large-row variants plain write-back stores are ~4 % faster than the
+// streaming hint (st.global.cs), for Small (tiny rows, many envs per warp) .cs is ~4 % faster.
+#define WH_ST(p, v) ::wh::st_obs<(RC == 4)>((p), (v))
+
 namespace wh {
 
 // Environment index inside one launch. 32-bit on purpose: every per-key element index (at most
 // e*R*R) then stays a single IMAD / IMAD.WIDE.U32; the launchers reject N*R*R >= 2^32.
 typedef uint32_t env_t;
+
+template <bool STREAM, typename T>
+__device__ __forceinline__ void st_obs(T *p, const T &v) {
+    if (STREAM) __stcs(p, v);
+    else *p = v;
+}
 
 constexpr uint32_t FULL = 0xffffffffu;
 constexpr uint32_t ABSENT_MOVE = 0xffffffffu;
@@ -530,7 +541,7 @@ __device__ __forceinline__ void build_obs(const KParams &P, const Group<GC> &g, 
         const bool writer = !g.ghost && g.gl < RC - 1;   // ghost lanes shadow group 0: keep them off its stage
 #pragma unroll
         for (int a = 0; a < RC; ++a) {
-            if (live && g.gl < RC) __stcs(orq + a * RC, rq);                    // core.py:429
+            if (live && g.gl < RC) WH_ST(orq + a * RC, rq);                    // core.py:429
             if (writer) {
                 const bool sh = g.gl >= a;                                      // core.py:426-427
                 s_pos[a * (RC - 1) + g.gl] = sh ? nx_p : my_p;
@@ -542,12 +553,12 @@ __device__ __forceinline__ void build_obs(const KParams &P, const Group<GC> &g, 
 #pragma unroll
             for (int k = 0; k < (St::ROWS / 2 + GC - 1) / GC; ++k) {
                 const int i = g.gl + k * GC;
-                if (i < St::ROWS / 2) __stcs(d_pos + i, reinterpret_cast<const int4 *>(stage)[i]);
+                if (i < St::ROWS / 2) WH_ST(d_pos + i, reinterpret_cast<const int4 *>(stage)[i]);
             }
 #pragma unroll
             for (int k = 0; k < (St::ROWS / 4 + GC - 1) / GC; ++k) {
                 const int i = g.gl + k * GC;
-                if (i < St::ROWS / 4) __stcs(d_av + i, reinterpret_cast<const int32_t *>(s_av)[i]);
+                if (i < St::ROWS / 4) WH_ST(d_av + i, reinterpret_cast<const int32_t *>(s_av)[i]);
             }
         }
         __syncwarp();
@@ -560,7 +571,7 @@ __device__ __forceinline__ void build_obs(const KParams &P, const Group<GC> &g, 
 #pragma unroll
                 for (int k = 0; k < (St::ROWS / 2 + GC - 1) / GC; ++k) {
                     const int i = g.gl + k * GC;
-                    if (i < St::ROWS / 2) __stcs(d_tgt + i, reinterpret_cast<const int4 *>(stage)[i % (RC - 1)]);
+                    if (i < St::ROWS / 2) WH_ST(d_tgt + i, reinterpret_cast<const int4 *>(stage)[i % (RC - 1)]);
                 }
             }
         } else {
@@ -572,7 +583,7 @@ __device__ __forceinline__ void build_obs(const KParams &P, const Group<GC> &g, 
 #pragma unroll
                 for (int k = 0; k < (St::ROWS / 2 + GC - 1) / GC; ++k) {
                     const int i = g.gl + k * GC;
-                    if (i < St::ROWS / 2) __stcs(d_tgt + i, reinterpret_cast<const int4 *>(stage)[i]);
+                    if (i < St::ROWS / 2) WH_ST(d_tgt + i, reinterpret_cast<const int4 *>(stage)[i]);
                 }
             }
         }
@@ -585,11 +596,11 @@ __device__ __forceinline__ void build_obs(const KParams &P, const Group<GC> &g, 
     for (int a = 0; a < RR; ++a) {
         if (g.gl < R - 1) {
             const bool sh = g.gl >= a;                                          // core.py:426-427
-            __stcs(op + a * (R - 1), sh ? nx_p : my_p);
-            __stcs(oa + a * (R - 1), (int8_t)(sh ? nx_a : my_a));
-            __stcs(ot + a * (R - 1), flavour == WH_OBS_STEP ? t_fixed : (sh ? nx_t : my_t));
+            WH_ST(op + a * (R - 1), sh ? nx_p : my_p);
+            WH_ST(oa + a * (R - 1), (int8_t)(sh ? nx_a : my_a));
+            WH_ST(ot + a * (R - 1), flavour == WH_OBS_STEP ? t_fixed : (sh ? nx_t : my_t));
         }
-        if (g.gl < R) __stcs(orq + a * R, rq);                                  // core.py:429
+        if (g.gl < R) WH_ST(orq + a * R, rq);                                  // core.py:429
     }
 }
 
@@ -674,9 +685,9 @@ __device__ __forceinline__ void build_obs_flat(const KParams &P, const Group<GC>
                 const int nvec = rows * St::F / St::VEC;
                 float *dst = env_out + a0 * St::F;
                 for (int i = g.gl; i < nvec; i += GC) {
-                    if (St::VEC == 4) __stcs(reinterpret_cast<float4 *>(dst) + i, reinterpret_cast<const float4 *>(stage)[i]);
-                    else if (St::VEC == 2) __stcs(reinterpret_cast<float2 *>(dst) + i, reinterpret_cast<const float2 *>(stage)[i]);
-                    else __stcs(dst + i, stage[i]);
+                    if (St::VEC == 4) WH_ST(reinterpret_cast<float4 *>(dst) + i, reinterpret_cast<const float4 *>(stage)[i]);
+                    else if (St::VEC == 2) WH_ST(reinterpret_cast<float2 *>(dst) + i, reinterpret_cast<const float2 *>(stage)[i]);
+                    else WH_ST(dst + i, stage[i]);
                 }
             }
             __syncwarp();
