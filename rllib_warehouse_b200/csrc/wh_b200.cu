@@ -374,6 +374,7 @@ int wh_reset(const wh_config *cfg, const wh_state *st, int64_t n_envs, int64_t e
              const int8_t *num_agents, const uint8_t *env_mask, const wh_obs *obs, void *stream) {
     KParams K; Shape sh;
     if (int rc = fill_params(cfg, K, sh)) return rc;
+    if (n_envs == 0) return 0;   // empty batch: nothing to launch
     if (!state_ok(st) || (obs && !obs_ok(obs))) return WH_E_ARG;
     if (agent_pos && (!init_pickups || !init_targets)) return WH_E_ARG;
     set_state(K, st);
@@ -391,6 +392,7 @@ int wh_step(const wh_config *cfg, const wh_state *st, int64_t n_envs, int64_t en
             const wh_obs *obs, int flags, void *stream) {
     KParams K; Shape sh;
     if (int rc = fill_params(cfg, K, sh)) return rc;
+    if (n_envs == 0) return 0;   // empty batch: nothing to launch
     if (!state_ok(st) || !actions || !rewards || !dones || (obs && !obs_ok(obs))) return WH_E_ARG;
     if ((spawn_pickups == nullptr) != (spawn_targets == nullptr)) return WH_E_ARG;
     if ((flags & WH_FLAG_AUTO_RESET) && spawn_pickups) return WH_E_ARG;  // auto-reset needs the native RNG
@@ -407,6 +409,7 @@ int wh_step_flat(const wh_config *cfg, const wh_state *st, int64_t n_envs, int64
                  unsigned long long *stats, float *flat_obs, int flags, void *stream) {
     KParams K; Shape sh;
     if (int rc = fill_params(cfg, K, sh)) return rc;
+    if (n_envs == 0) return 0;   // empty batch: nothing to launch
     if (!state_ok(st) || !actions || !rewards || !dones || !flat_obs) return WH_E_ARG;
     set_state(K, st);
     K.flat_out = flat_obs;
@@ -422,6 +425,7 @@ int wh_greedy_step(const wh_config *cfg, const wh_state *st, int64_t n_envs, int
                    unsigned long long *stats, const wh_obs *obs, int flags, void *stream) {
     KParams K; Shape sh;
     if (int rc = fill_params(cfg, K, sh)) return rc;
+    if (n_envs == 0) return 0;   // empty batch: nothing to launch
     if (!state_ok(st) || !rewards || !dones || (obs && !obs_ok(obs))) return WH_E_ARG;
     set_state(K, st);
     if (obs) K.obs = *obs;
@@ -435,6 +439,7 @@ int wh_build_obs(const wh_config *cfg, const wh_state *st, int64_t n_envs, int f
                  const wh_obs *obs, void *stream) {
     KParams K; Shape sh;
     if (int rc = fill_params(cfg, K, sh)) return rc;
+    if (n_envs == 0) return 0;   // empty batch: nothing to launch
     if (!state_ok(st) || !obs_ok(obs) || (flavour != WH_OBS_STEP && flavour != WH_OBS_RESET)) return WH_E_ARG;
     set_state(K, st);
     K.obs = *obs; K.N = n_envs; K.flavour = flavour;
@@ -445,6 +450,7 @@ int wh_build_obs_flat(const wh_config *cfg, const wh_state *st, int64_t n_envs, 
                       float *out, void *stream) {
     KParams K; Shape sh;
     if (int rc = fill_params(cfg, K, sh)) return rc;
+    if (n_envs == 0) return 0;   // empty batch: nothing to launch
     if (!state_ok(st) || !out || (flavour != WH_OBS_STEP && flavour != WH_OBS_RESET)) return WH_E_ARG;
     set_state(K, st);
     K.flat_out = out;
@@ -458,6 +464,7 @@ int wh_greedy(const wh_config *cfg, const wh_obs *obs, const int8_t *num_agents,
               const int32_t *random_actions, int32_t *actions, void *stream) {
     KParams K; Shape sh;
     if (int rc = fill_params(cfg, K, sh)) return rc;
+    if (n_envs == 0) return 0;   // empty batch: nothing to launch
     if (!obs || !obs->requests || !obs->self_position || !obs->self_availability ||
         !obs->self_delivery_target || !num_agents || !actions)
         return WH_E_ARG;
@@ -528,6 +535,7 @@ int wh_env_create(const wh_config *cfg, int64_t n_envs, int device, int64_t env_
     if (!cfg || !out || n_envs <= 0) return WH_E_ARG;
     KParams K; Shape sh;
     if (int rc = fill_params(cfg, K, sh)) return rc;
+    if (n_envs == 0) return 0;   // empty batch: nothing to launch
     CK(cudaSetDevice(device));
     wh_env *E = new (std::nothrow) wh_env();
     if (!E) return WH_E_ARG;

@@ -309,3 +309,70 @@ def test_cuda_graph_replay_matches_eager():
             eager.step(acts[t])
     for k in eager.state:
         assert torch.equal(eager.state[k], graphed.state[k]), k
+
+
+def test_full_size_properties_and_oracle_prefix():
+    """BASELINE configs[3] at its FULL size (Large, 262 144 envs, 205 greedy steps with auto-reset):
+    size-independent invariants on the whole batch, and — because the RNG is keyed by the global
+    env id — a bit-exact comparison of the first 2 048 envs with the CPU oracle."""
+    from rllib_warehouse_b200 import LARGE, BatchedWarehouse
+    n, m = 262144, 2048
+    gpu = BatchedWarehouse(LARGE, n, seed=20261018, auto_reset=True)
+    cpu = wo.OracleEnv(wo.variant_config("large"), m, seed=20261018)
+    gpu.reset(); cpu.reset()
+    R, dim = gpu.R, LARGE.area_dimension
+    total_reward = torch.zeros((), dtype=torch.float64, device=gpu.device)
+    for t in range(205):
+        obs, rew, dones = gpu.greedy_step()
+        total_reward += rew.sum()
+        cpu.greedy(); cpu.step(cpu.actions)
+        if cpu.dones.all():
+            cpu.reset(env_mask=cpu.dones)
+        if t % 40 == 0 or t in (198, 199, 200, 204):
+            st = gpu.state
+            assert bool(((st["pickup_tgt"] > -1).sum(dim=1) == R).all()), "exactly R active requests (core.py:338-351)"
+            assert bool(((st["pickup_timer"] > 0) == (st["pickup_tgt"] > -1)).all())
+            pos = st["agent_pos"]
+            assert bool(((pos >= 0) & (pos < dim)).all()) and bool(((rew == 0) | (rew == 1)).all())
+            assert bool((dones == dones[0]).all()) and bool((st["time"] == st["time"][0]).all())
+            req = obs["requests"]
+            assert bool((req[:, 0] == req[:, 5]).all()), "requests identical for every agent of an env (core.py:429)"
+            cells = (req[:, 0, :, 0] * 32 + req[:, 0, :, 1]).sort(dim=1).values
+            assert bool((cells.diff(dim=1) > 0).all()), "the R waiting requests sit on R distinct pickup cells"
+            for k in ("agent_pos", "agent_tgt", "pickup_tgt", "pickup_timer", "time", "episode"):
+                got = st[k][:m].to(torch.int32).cpu().numpy()
+                assert np.array_equal(got.reshape(cpu.state[k].shape), cpu.state[k]), (t, k)
+    s = gpu.stats.cpu().numpy()
+    assert s[0] == n and s[1] == s[2] + s[3]
+    acc = gpu.state["acc"].sum(dim=0).cpu().numpy()          # the 5 steps of the second episode
+    assert float(total_reward.item()) == float(s[1] + acc[0] + acc[1])
+    assert np.array_equal(cpu.stats[:5], gpu_prefix_stats(LARGE, m, 20261018))
+
+
+def gpu_prefix_stats(cfg, m, seed):
+    from rllib_warehouse_b200 import BatchedWarehouse
+    g = BatchedWarehouse(cfg, m, seed=seed, auto_reset=True)
+    g.reset()
+    for _ in range(205):
+        g.greedy_step(with_obs=False, want_actions=False)
+    return g.stats[:5].cpu().numpy()
+
+
+def test_limits_and_empty_batch():
+    """Largest supported geometry (R = 32, P = D = 64: one env per warp) and an empty batch."""
+    from rllib_warehouse_b200 import BatchedWarehouse, WarehouseConfig
+    R, dim, racks = 32, 20, (4, 8, 12, 16)
+    n = 65
+    gpu = BatchedWarehouse(WarehouseConfig(R, dim, racks, 30, 7, R), n, num_agents=29, seed=8, auto_reset=True)
+    cpu = wo.OracleEnv(wo.make_config(R, dim, list(racks), 30, 7), n, num_agents=29, seed=8)
+    gpu.reset(); cpu.reset()
+    same_state(gpu, cpu, "R=32 reset"); same_obs(gpu, cpu, "R=32 reset")
+    rng = np.random.Generator(np.random.PCG64(5))
+    for t in range(29):
+        a = rng.integers(-1, 9, size=(n, R)).astype(np.int32) if t % 2 else gpu.greedy_actions().cpu().numpy()
+        gpu.step(a); cpu.step(a)
+        same_state(gpu, cpu, f"R=32 step {t}"); same_obs(gpu, cpu, f"R=32 step {t}")
+        assert torch.equal(gpu.build_obs_flat(), gpu.flatten_obs(gpu.obs))
+    empty = BatchedWarehouse(WarehouseConfig(4, 12, (4, 8)), 0)
+    empty.reset(); empty.step(torch.zeros((0, 4), dtype=torch.int32)); empty.greedy_step(); empty.build_obs_flat()
+    assert empty.obs["requests"].shape == (0, 4, 4, 4)
