@@ -9,7 +9,7 @@
  *
  * Parity pinning: the reference ships no tests or golden vectors, so this oracle
  * is pinned against fixtures produced by EXECUTING the unmodified reference
- * (oracle/make_golden.py -> tests/golden/*.npz; checked by tests/test_oracle_golden.py) and, in
+ * (oracle/make_golden.py -> the .npz fixtures under tests/golden; checked by tests/test_oracle_golden.py) and, in
  * the build container, against the live reference (tests/test_oracle_vs_reference.py).
  *
  * All state is held at the reference's own width (int32) so that every array can be compared
@@ -98,10 +98,12 @@ int who_greedy(const who_config *cfg, const who_obs *obs, const int32_t *num_age
                int64_t n_envs, int64_t env_id0, uint64_t seed, uint64_t rand_threshold,
                const uint8_t *is_random, const int32_t *random_actions, int32_t *actions);
 
-/* Multi-threaded rollout used as the CPU baseline: n_steps of {greedy | preset random actions}
- * -> step -> build_obs over all envs with `n_threads` pthreads, envs partitioned contiguously.
- * policy: 0 = actions given per step in actions_seq [n_steps? no: reused each step] (random), 1 = greedy.
- * Returns total agent-steps executed. */
+/* Multi-threaded rollout used as the CPU baseline: n_steps of {policy} -> step -> build_obs over all
+ * envs with `n_threads` pthreads, envs partitioned contiguously (no synchronisation between
+ * threads: envs are independent). policy 0: the given `actions` [N,R] are applied at every step
+ * (random-action workload); policy 1: the greedy solver on the previous observations, written to
+ * actions_scratch [N,R]. auto_reset: finished envs are reset with the native RNG and get their
+ * reset observation. Returns the total number of agent-steps executed. */
 int64_t who_rollout(const who_config *cfg, who_state *st, who_obs *obs, int64_t n_envs,
                     int64_t env_id0, uint64_t seed, int policy, const int32_t *actions,
                     int32_t *actions_scratch, float *rewards, uint8_t *dones, int64_t *stats,
