@@ -65,7 +65,7 @@ def cpu_rollout_rate(variant, n_envs, steps, threads, seed, policy="random", war
     env = wo.OracleEnv(wo.variant_config(variant), n_envs, seed=seed)
     env.reset()
     rng = np.random.Generator(np.random.PCG64(seed))
-    actions = rng.integers(0, 9, size=(n_envs, env.R)).astype(np.int32)
+    actions = rng.integers(0, 9, size=(16, n_envs, env.R)).astype(np.int32)   # 16 distinct action sets, cycled
     env.rollout(warmup, threads, policy=policy, actions=actions)
     t0 = time.perf_counter()
     agent_steps = env.rollout(steps, threads, policy=policy, actions=actions)
@@ -140,7 +140,7 @@ def run_reference(args):
     env = wo.OracleEnv(wo.variant_config(args.variant), n, seed=args.seed)
     env.reset()
     rng = np.random.Generator(np.random.PCG64(args.seed))
-    actions = rng.integers(0, 9, size=(n, env.R)).astype(np.int32)
+    actions = rng.integers(0, 9, size=(16, n, env.R)).astype(np.int32)        # 16 distinct action sets, cycled
     env.rollout(args.warmup, threads, policy="random", actions=actions)
     t0 = time.perf_counter()
     agent_steps = env.rollout(args.steps, threads, policy="random", actions=actions)

@@ -431,7 +431,7 @@ int who_greedy(const who_config *cfg, const who_obs *obs, const int32_t *num_age
 /* ------------------------------------------------------------------------------------------ */
 typedef struct {
     const who_config *cfg; who_state *st; who_obs *obs;
-    int64_t e0, e1, env_id0; uint64_t seed; int policy; const int32_t *actions;
+    int64_t e0, e1, env_id0, n_envs; uint64_t seed; int policy, n_action_sets; const int32_t *actions;
     int32_t *scratch; float *rewards; uint8_t *dones; int64_t stats[WHO_NUM_STATS];
     int n_steps, auto_reset; int64_t agent_steps;
 } job_t;
@@ -440,7 +440,7 @@ static void *rollout_thread(void *arg) {
     job_t *j = (job_t *)arg;
     for (int s = 0; s < j->n_steps; ++s) {
         for (int64_t e = j->e0; e < j->e1; ++e) {
-            const int32_t *act = j->actions;
+            const int32_t *act = j->actions + (int64_t)(s % j->n_action_sets) * j->n_envs * j->cfg->num_requests;
             if (j->policy == 1) {
                 greedy_one(j->cfg, j->obs, j->st->num_agents, j->st->episode, j->st->time, e,
                            j->env_id0 + e, j->seed ^ 0x5EEDull, 0, NULL, NULL, j->scratch);
@@ -463,7 +463,7 @@ static void *rollout_thread(void *arg) {
 int64_t who_rollout(const who_config *cfg, who_state *st, who_obs *obs, int64_t n_envs,
                     int64_t env_id0, uint64_t seed, int policy, const int32_t *actions,
                     int32_t *actions_scratch, float *rewards, uint8_t *dones, int64_t *stats,
-                    int n_steps, int n_threads, int auto_reset) {
+                    int n_steps, int n_threads, int auto_reset, int n_action_sets) {
     if (check_cfg(cfg) || n_threads < 1) return -1;
     if (n_threads > n_envs) n_threads = (int)n_envs;
     job_t *jobs = (job_t *)calloc((size_t)n_threads, sizeof(job_t));
@@ -473,6 +473,7 @@ int64_t who_rollout(const who_config *cfg, who_state *st, who_obs *obs, int64_t 
         j->cfg = cfg; j->st = st; j->obs = obs;
         j->e0 = n_envs * t / n_threads; j->e1 = n_envs * (t + 1) / n_threads;
         j->env_id0 = env_id0; j->seed = seed; j->policy = policy; j->actions = actions;
+        j->n_envs = n_envs; j->n_action_sets = n_action_sets > 0 ? n_action_sets : 1;
         j->scratch = actions_scratch; j->rewards = rewards; j->dones = dones;
         j->n_steps = n_steps; j->auto_reset = auto_reset;
     }

@@ -100,14 +100,14 @@ int who_greedy(const who_config *cfg, const who_obs *obs, const int32_t *num_age
 
 /* Multi-threaded rollout used as the CPU baseline: n_steps of {policy} -> step -> build_obs over all
  * envs with `n_threads` pthreads, envs partitioned contiguously (no synchronisation between
- * threads: envs are independent). policy 0: the given `actions` [N,R] are applied at every step
- * (random-action workload); policy 1: the greedy solver on the previous observations, written to
+ * threads: envs are independent). policy 0: `actions` [n_action_sets,N,R], step s applies set
+ * s % n_action_sets (random-action workload); policy 1: the greedy solver on the previous observations, written to
  * actions_scratch [N,R]. auto_reset: finished envs are reset with the native RNG and get their
  * reset observation. Returns the total number of agent-steps executed. */
 int64_t who_rollout(const who_config *cfg, who_state *st, who_obs *obs, int64_t n_envs,
                     int64_t env_id0, uint64_t seed, int policy, const int32_t *actions,
                     int32_t *actions_scratch, float *rewards, uint8_t *dones, int64_t *stats,
-                    int n_steps, int n_threads, int auto_reset);
+                    int n_steps, int n_threads, int auto_reset, int n_action_sets);
 
 /* Raw Philox4x32-10 block, exported so tests can check the CUDA RNG directly. */
 void who_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint64_t seed, uint32_t out[4]);

@@ -185,11 +185,12 @@ class OracleEnv:
     def rollout(self, n_steps, n_threads, policy="greedy", actions=None, auto_reset=True):
         st, ob = self._st(), self._ob()
         actions = _i32(actions)
+        n_sets = 1 if actions is None or actions.ndim < 3 else actions.shape[0]
         n = lib().who_rollout(C.byref(self.cfg), C.byref(st), C.byref(ob), C.c_int64(self.N),
                               C.c_int64(self.env_id0), C.c_uint64(self.seed),
                               C.c_int(1 if policy == "greedy" else 0), _p(actions), _p(self.actions),
                               _p(self.rewards), _p(self.dones), _p(self.stats), C.c_int(n_steps),
-                              C.c_int(n_threads), C.c_int(int(auto_reset)))
+                              C.c_int(n_threads), C.c_int(int(auto_reset)), C.c_int(n_sets))
         assert n >= 0, n
         return int(n)
 
