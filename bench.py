@@ -149,7 +149,7 @@ def run_reference(args):
     sample = (f"oracle/wh_oracle.c (C port of the reference step+obs; the Python reference cannot travel to "
               f"the GPU box), bounded sample: {n} {args.variant} envs per step instead of the config's "
               f"envs_total, random actions, {threads} pthreads")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "agent_steps_per_sec", "value": rate, "unit": "agent-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": args.scaling,
@@ -157,7 +157,7 @@ def run_reference(args):
         "config": workload_config(args, max(1, args.gpus)),
         "cpu_baseline": {"value": rate, "unit": "agent-steps/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def workload_config(args, world):
@@ -398,7 +398,7 @@ def run_b200(args):
         out["cpu_baseline"] = cpu_baseline(args, args.cpu_seconds)
     out["stats"] = {k: v for k, v in env.stats_dict(stats).items() if not k.startswith("avg_agent_reward_") or k.endswith("_all")}
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -467,7 +467,30 @@ def extras(args, dev, peak):
     return res
 
 
+_REAL_STDOUT = None
+
+
+def _protect_stdout():
+    """stdout must carry exactly ONE JSON line, but NCCL / torch print banners ("NCCL version ...")
+    to fd 1 from C++. Point fd 1 at stderr for the whole run and keep the real stdout for emit()."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, line)
+
+
 def main():
+    _protect_stdout()
     args = parse()
     if args.impl == "reference":
         run_reference(args)
