@@ -376,3 +376,47 @@ def test_limits_and_empty_batch():
     empty = BatchedWarehouse(WarehouseConfig(4, 12, (4, 8)), 0)
     empty.reset(); empty.step(torch.zeros((0, 4), dtype=torch.int32)); empty.greedy_step(); empty.build_obs_flat()
     assert empty.obs["requests"].shape == (0, 4, 4, 4)
+
+
+def test_random_geometries_fuzz():
+    """Seeded fuzz over the whole supported configuration space (R 2..32, 1..4 racks at arbitrary —
+    also adjacent, i.e. overlapping-cell — positions, dim up to 20, short waits/episodes, partial
+    agent counts): native RNG, random absent agents and dict orders, auto-reset; state, obs,
+    rewards, dones and stats must equal the C oracle's."""
+    from rllib_warehouse_b200 import BatchedWarehouse, WarehouseConfig
+    rng = np.random.Generator(np.random.PCG64(2026))
+    tried = 0
+    while tried < 14:
+        L = int(rng.integers(1, 5))
+        dim = int(rng.integers(9, 21))
+        racks = sorted(rng.choice(np.arange(2, dim - 1), size=L, replace=False).tolist())
+        P, D = 4 * L * L, 4 * (dim - 4)
+        R = int(rng.integers(2, min(32, P, D) + 1))
+        episode, wait = int(rng.integers(5, 30)), int(rng.integers(1, 12))
+        A = int(rng.integers(1, R + 1))
+        train = bool(rng.integers(0, 2))
+        tried += 1
+        n = int(rng.integers(1, 200))
+        cfg = WarehouseConfig(R, dim, tuple(racks), episode, wait, R, train)
+        gpu = BatchedWarehouse(cfg, n, num_agents=A, seed=tried, auto_reset=True)
+        cpu = wo.OracleEnv(wo.make_config(R, dim, racks, episode, wait, random_num_agents=train), n, num_agents=A, seed=tried)
+        gpu.reset(); cpu.reset()
+        tag = f"cfg R={R} dim={dim} racks={racks} ep={episode} wait={wait} A={A} train={train} n={n}"
+        same_state(gpu, cpu, tag + " reset"); same_obs(gpu, cpu, tag + " reset")
+        for t in range(episode + 4):
+            a = rng.integers(-1, 9, size=(n, R)).astype(np.int32)
+            order = np.stack([rng.permutation(R) for _ in range(n)]).astype(np.int32) if t % 2 else None
+            gpu.step(a, order=order)
+            cpu.step(a, order=order, with_obs=False)
+            rew, done = cpu.rewards.copy(), cpu.dones.astype(bool)
+            cpu.build_obs(0)
+            if done.any():
+                step_obs = {k: v.copy() for k, v in cpu.obs.items()}
+                cpu.reset(env_mask=done.astype(np.uint8))
+                for k in cpu.obs:
+                    step_obs[k][done] = cpu.obs[k][done]
+                    cpu.obs[k][...] = step_obs[k]
+            same_state(gpu, cpu, f"{tag} step {t}"); same_obs(gpu, cpu, f"{tag} step {t}")
+            assert np.array_equal(gpu.rewards.cpu().numpy(), rew), f"{tag} step {t}"
+            assert np.array_equal(gpu.dones.cpu().numpy().astype(bool), done), f"{tag} step {t}"
+        assert np.array_equal(gpu.stats.cpu().numpy(), cpu.stats), tag
