@@ -451,6 +451,34 @@ def extras(args, dev, peak):
         }
         del env
         torch.cuda.empty_cache()
+    # Proxy for BASELINE configs[4] (RLlib PPO rollouts; ray is not installed): sampling with an
+    # on-device torch policy (2x256 MLP, bf16, argmax) fed by the step kernel's flattened observations.
+    # The policy GEMMs are library code (cuBLAS through torch); the env side is this repo's kernels.
+    try:
+        n = 65536
+        env = BatchedWarehouse(VARIANTS["large"], n, device=dev, seed=args.seed + 3, auto_reset=True)
+        env.reset()
+        F = 9 * env.R + 1
+        torch.manual_seed(0)
+        policy = torch.nn.Sequential(torch.nn.Linear(F, 256), torch.nn.ReLU(), torch.nn.Linear(256, 256),
+                                     torch.nn.ReLU(), torch.nn.Linear(256, 9)).to(dev, torch.bfloat16)
+        flat = [env.build_obs_flat(1)]
+
+        def sample(i):
+            with torch.no_grad():
+                logits = policy(flat[0].view(-1, F).to(torch.bfloat16))
+                actions = logits.argmax(dim=-1).view(n, env.R).to(torch.int32)
+            flat[0], _, _ = env.step_flat(actions)
+
+        ms_pol = _time_steps(sample, 50, 5)
+        res["configs4_proxy_torch_policy_rollout"] = {
+            "ms": ms_pol, "agent_steps_per_sec": n * 16 / (ms_pol * 1e-3), "envs": n,
+            "note": "large, 65 536 envs; per step: wh_step_flat + bf16 MLP 145-256-256-9 over 1 048 576 agent rows + argmax",
+        }
+        del env, policy, flat
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001
+        res["configs4_proxy_torch_policy_rollout"] = {"error": repr(e)}
     # BASELINE configs[1] shape (Small, 4 096 envs): launch-bound eagerly, so also as a CUDA graph
     from rllib_warehouse_b200 import StepGraph
     env = BatchedWarehouse(VARIANTS["small"], 4096, device=dev, seed=args.seed + 2, auto_reset=True)

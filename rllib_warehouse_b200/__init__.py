@@ -12,11 +12,12 @@ from .variants import (WarehouseLarge, WarehouseLargeTrain, WarehouseMedium, War
                        WarehouseSmall, WarehouseSmallTrain)
 from .solvers import BatchedGreedySolver, WarehouseRandomGreedySolver, WarehouseSolver
 from .vector_env import WarehouseVectorEnv
+from .host_env import HostWarehouse
 
 __all__ = [
     "Warehouse", "WarehouseSmall", "WarehouseMedium", "WarehouseLarge",
     "WarehouseSmallTrain", "WarehouseMediumTrain", "WarehouseLargeTrain",
     "WarehouseConfig", "SMALL", "MEDIUM", "LARGE", "VARIANTS",
-    "BatchedWarehouse", "StepGraph", "WarehouseVectorEnv", "BatchedGreedySolver", "WarehouseRandomGreedySolver", "WarehouseSolver",
+    "BatchedWarehouse", "StepGraph", "HostWarehouse", "WarehouseVectorEnv", "BatchedGreedySolver", "WarehouseRandomGreedySolver", "WarehouseSolver",
 ]
 name = "rllib_warehouse_b200"

@@ -184,3 +184,28 @@ def test_batched_rollout_driver_with_torch_policy(tmp_path):
                              capture_output=True, text=True, timeout=300)
         assert res.returncode == 0, res.stderr[-3000:]
         assert "episodes: 2048" in res.stdout and "avg_agent_reward_all" in res.stdout, res.stdout
+
+
+@pytest.mark.parametrize("compact", [False, True])
+def test_host_warehouse_numpy_api(compact):
+    """HostWarehouse (numpy in / numpy out over the wh_env_* layer) against BatchedWarehouse."""
+    import torch
+    from rllib_warehouse_b200 import SMALL, BatchedWarehouse, HostWarehouse
+    n = 1001
+    host = HostWarehouse(SMALL, n, seed=6, chunks=3, compact=compact)
+    twin = BatchedWarehouse(SMALL, n, seed=6, auto_reset=True)
+    host.reset(); twin.reset()
+    rng = np.random.Generator(np.random.PCG64(1))
+    for t in range(203):
+        a = rng.integers(-1, 9, size=(n, 4))
+        rew, dones, obs = host.step(a, with_obs=(not compact and t % 67 == 0))
+        twin.step(a.astype(np.int32))
+        assert np.array_equal(rew, twin.rewards.cpu().numpy()) and np.array_equal(dones, twin.dones.cpu().numpy().astype(bool))
+        if obs is not None:
+            for k, v in obs.items():
+                assert np.array_equal(v, twin.obs[k].cpu().numpy()), k
+    dev_obs = host.obs_tensors()
+    for k, v in dev_obs.items():
+        assert torch.equal(v, twin.obs[k]), k
+    assert np.array_equal(host.stats(), twin.stats.cpu().numpy())
+    host.close()
