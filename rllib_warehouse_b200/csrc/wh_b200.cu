@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(BLOCK, (RC == 16 ? WH_MIN_BLOCKS_LARGE : RC ==
     const env_t e = t.e;
     const uint32_t env_id = (uint32_t)P.env_id0 + e;
     EnvRegs s;
-    load_env(P, g, e, R, s);
+    load_env(P, g, e, R, (RC ? 4 * GC : P.P), s);
 
     int act = -1, ord = -1;
     if (GREEDY) {
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(BLOCK, (RC == 16 ? WH_MIN_BLOCKS_LARGE : RC ==
         if (done) { active = a2; flavour = WH_OBS_RESET; }
         meta = true;
     }
-    if (t.live) store_env(P, g, e, R, s, meta);
+    if (t.live) store_env(P, g, e, R, (RC ? 4 * GC : P.P), s, meta);
     if (FLAT)   // RLlib-flattened float32 layout instead of the dict keys (separate instantiation)
         build_obs_flat<GC, RC>(P, g, e, R, s, active, tpos16, flavour, t.live, P.flat_out,
                                reinterpret_cast<float *>(StageMem<GC, RC, true>::mine(smem, g)));
@@ -139,12 +139,12 @@ __global__ void __launch_bounds__(BLOCK) k_reset(const __grid_constant__ KParams
     const int R = RC ? RC : P.R;
     const env_t e = t.e;
     EnvRegs s;
-    load_env(P, g, e, R, s);
+    load_env(P, g, e, R, (RC ? 4 * GC : P.P), s);
     const bool doit = t.live && (!P.env_mask || P.env_mask[e]);
     const unsigned long long active =
         do_reset(P, g, e, R, (uint32_t)P.env_id0 + e, s, P.r_agent_pos != nullptr, doit);
     if (doit) {
-        store_env(P, g, e, R, s, true);
+        store_env(P, g, e, R, (RC ? 4 * GC : P.P), s, true);
         if (g.gl == 0) reinterpret_cast<int4 *>(P.acc)[e] = make_int4(0, 0, 0, 0);
     }
     if (P.obs.requests) build_obs<GC, RC>(P, g, e, R, s, active, 0u, WH_OBS_RESET, doit, StageMem<GC, RC>::mine(smem, g));
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(BLOCK) k_obs(const __grid_constant__ KParams P
     const Tile<GC> t(P, g);
     const int R = RC ? RC : P.R;
     EnvRegs s;
-    load_env(P, g, t.e, R, s);
+    load_env(P, g, t.e, R, (RC ? 4 * GC : P.P), s);
     const unsigned long long active = active_mask(g, s.pt4);
     build_obs<GC, RC>(P, g, t.e, R, s, active, target_cell16(P, s.atgt), P.flavour, t.live, StageMem<GC, RC>::mine(smem, g));
 }
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(BLOCK) k_obs_flat(const __grid_constant__ KPar
     const Tile<GC> t(P, g);
     const int R = RC ? RC : P.R;
     EnvRegs s;
-    load_env(P, g, t.e, R, s);
+    load_env(P, g, t.e, R, (RC ? 4 * GC : P.P), s);
     const unsigned long long active = active_mask(g, s.pt4);
     build_obs_flat<GC, RC>(P, g, t.e, R, s, active, target_cell16(P, s.atgt), P.flavour, t.live,
                            P.flat_out, reinterpret_cast<float *>(StageMem<GC, RC, true>::mine(smem, g)));
@@ -283,9 +283,10 @@ static int fill_params(const wh_config *cfg, KParams &K, Shape &sh) {
     K.G = G;
     K.invL = (256 + K.L - 1) / K.L;
     sh.G = G; sh.RC = 0;
-    if (K.R == 4 && G == 4) sh.RC = 4;       // WarehouseSmall
-    if (K.R == 9 && G == 9) sh.RC = 9;       // WarehouseMedium: 3 envs per warp
-    if (K.R == 16 && G == 16) sh.RC = 16;    // WarehouseLarge
+    // compile-time-shaped kernels need R == G and P == 4G (every lane owns one agent and 4 points)
+    if (K.R == 4 && G == 4 && K.P == 16) sh.RC = 4;        // WarehouseSmall
+    if (K.R == 9 && G == 9 && K.P == 36) sh.RC = 9;        // WarehouseMedium: 3 envs per warp
+    if (K.R == 16 && G == 16 && K.P == 64) sh.RC = 16;     // WarehouseLarge
     return 0;
 }
 

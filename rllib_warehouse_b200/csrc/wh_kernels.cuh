@@ -120,11 +120,22 @@ __device__ __forceinline__ int nth_set64(unsigned long long m, int n) {
     return pos;
 }
 
+// r-th set bit when r < RMAX is tiny (Small): strip the lowest set bit r times, then find-first-set
+template <int RMAX>
+__device__ __forceinline__ int nth_set_small(uint32_t m, int r) {
+#pragma unroll
+    for (int i = 0; i < RMAX - 1; ++i)
+        if (r > i) m &= m - 1u;
+    return __ffs((int)m) - 1;
+}
+
 // core.py:178-188  delivery point d -> cell, v = 2 + d/4, side = d%4: (v,0) (0,v) (v,dim-1) (dim-1,v)
 __device__ __forceinline__ uint32_t delivery_cell16(int d, int dim) {
+    // sides 0,2 (even): x = v, y = 0 | dim-1      sides 1,3 (odd): x = 0 | dim-1, y = v
     const int v = 2 + (d >> 2), s = d & 3;
-    const int x = (s == 1) ? 0 : (s == 3) ? dim - 1 : v;
-    const int y = (s == 0) ? 0 : (s == 2) ? dim - 1 : v;
+    const int edge = (s >> 1) * (dim - 1);
+    const bool odd = (s & 1) != 0;
+    const int x = odd ? edge : v, y = odd ? v : edge;
     return (uint32_t)x | ((uint32_t)y << 8);
 }
 
@@ -252,8 +263,9 @@ struct EnvRegs {
     int time, A, ep;
 };
 
+// PP = number of pickup points: a compile-time 4*G in the variant kernels, P.P otherwise
 template <int GC>
-__device__ __forceinline__ void load_env(const KParams &P, const Group<GC> &g, env_t e, int R, EnvRegs &s) {
+__device__ __forceinline__ void load_env(const KParams &P, const Group<GC> &g, env_t e, int R, int PP, EnvRegs &s) {
     s.time = P.time[e];
     s.A = P.num_agents[e];
     s.ep = P.episode_ctr[e];
@@ -265,27 +277,27 @@ __device__ __forceinline__ void load_env(const KParams &P, const Group<GC> &g, e
     }
     s.pt4 = 0xFFFFFFFFu;
     s.tm[0] = s.tm[1] = s.tm[2] = s.tm[3] = -1;
-    if (4 * g.gl < P.P) {
-        s.pt4 = reinterpret_cast<const uint32_t *>(P.pickup_tgt + e * P.P)[g.gl];
-        const uint2 t = reinterpret_cast<const uint2 *>(P.pickup_timer + e * P.P)[g.gl];
+    if (4 * g.gl < PP) {
+        s.pt4 = reinterpret_cast<const uint32_t *>(P.pickup_tgt + e * PP)[g.gl];
+        const uint2 t = reinterpret_cast<const uint2 *>(P.pickup_timer + e * PP)[g.gl];
         s.tm[0] = (int16_t)(t.x & 0xFFFF); s.tm[1] = (int16_t)(t.x >> 16);
         s.tm[2] = (int16_t)(t.y & 0xFFFF); s.tm[3] = (int16_t)(t.y >> 16);
     }
 }
 
 template <int GC>
-__device__ __forceinline__ void store_env(const KParams &P, const Group<GC> &g, env_t e, int R,
+__device__ __forceinline__ void store_env(const KParams &P, const Group<GC> &g, env_t e, int R, int PP,
                                           const EnvRegs &s, bool store_meta) {
     if (g.gl < R) {
         reinterpret_cast<uint16_t *>(P.agent_pos)[e * R + g.gl] = (uint16_t)s.pos16;
         P.agent_tgt[e * R + g.gl] = (int8_t)s.atgt;
     }
-    if (4 * g.gl < P.P) {
-        reinterpret_cast<uint32_t *>(P.pickup_tgt + e * P.P)[g.gl] = s.pt4;
+    if (4 * g.gl < PP) {
+        reinterpret_cast<uint32_t *>(P.pickup_tgt + e * PP)[g.gl] = s.pt4;
         uint2 t;
         t.x = (uint32_t)(s.tm[0] & 0xFFFF) | ((uint32_t)(s.tm[1] & 0xFFFF) << 16);
         t.y = (uint32_t)(s.tm[2] & 0xFFFF) | ((uint32_t)(s.tm[3] & 0xFFFF) << 16);
-        reinterpret_cast<uint2 *>(P.pickup_timer + e * P.P)[g.gl] = t;
+        reinterpret_cast<uint2 *>(P.pickup_timer + e * PP)[g.gl] = t;
     }
     if (g.gl == 0) {
         P.time[e] = s.time;
@@ -506,7 +518,8 @@ __device__ __forceinline__ void build_obs(const KParams &P, const Group<GC> &g, 
 
     // core.py:409-418 request list: active pickup points in ascending index, [px,py,dx,dy]
     const bool have = g.gl < R && g.gl < __popcll(active);
-    const int p = nth_set64<Group<GC>::PBITS>(active, have ? g.gl : 0) & 63;
+    const int p = ((RC != 0 && RC <= 4) ? nth_set_small<(RC ? RC : 1)>((uint32_t)active, have ? g.gl : 0)
+                                        : nth_set64<Group<GC>::PBITS>(active, have ? g.gl : 0)) & 63;
     const uint32_t w4 = g.shfl(s.pt4, p >> 2);
     int4 rq = make_int4(null_pos, null_pos, null_pos, null_pos);  // only if < R active (unreachable)
     if (have) {
@@ -634,7 +647,8 @@ __device__ __forceinline__ void build_obs_flat(const KParams &P, const Group<GC>
                           (((tpos >> 8) & 0x7Fu) << 21) | (avail << 28);
     const uint32_t next = g.shfl_down1(mine);
     const bool have = g.gl < R && g.gl < __popcll(active);
-    const int p = nth_set64<Group<GC>::PBITS>(active, have ? g.gl : 0) & 63;
+    const int p = ((RC != 0 && RC <= 4) ? nth_set_small<(RC ? RC : 1)>((uint32_t)active, have ? g.gl : 0)
+                                        : nth_set64<Group<GC>::PBITS>(active, have ? g.gl : 0)) & 63;
     const uint32_t w4 = g.shfl(s.pt4, p >> 2);
     float4 rq = make_float4((float)null_pos, (float)null_pos, (float)null_pos, (float)null_pos);
     if (have) {
