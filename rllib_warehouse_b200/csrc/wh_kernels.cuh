@@ -584,7 +584,11 @@ __device__ __forceinline__ void build_obs(const KParams &P, const Group<GC> &g, 
 #pragma unroll
                 for (int k = 0; k < (St::ROWS / 2 + GC - 1) / GC; ++k) {
                     const int i = g.gl + k * GC;
-                    if (i < St::ROWS / 2) WH_ST(d_tgt + i, reinterpret_cast<const int4 *>(stage)[i % (RC - 1)]);
+                    // i mod (RC-1): GC == RC here, so i = gl + k (mod RC-1) and gl + k < 2(RC-1)
+                    int src = g.gl + k * (GC % (RC - 1));
+                    if (src >= RC - 1) src -= RC - 1;
+                    if (src >= RC - 1) src -= RC - 1;
+                    if (i < St::ROWS / 2) WH_ST(d_tgt + i, reinterpret_cast<const int4 *>(stage)[src]);
                 }
             }
         } else {
