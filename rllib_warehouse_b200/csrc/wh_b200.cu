@@ -8,6 +8,9 @@
 #include <dlfcn.h>
 
 #include "wh_kernels.cuh"
+#ifdef WH_WITH_TPE
+#include "experimental/wh_tpe.cuh"   // thread-per-env kernels: bit-exact but slower, see the file header
+#endif
 
 namespace wh {
 
@@ -331,6 +334,30 @@ static void launch_greedy(const KParams &K, cudaStream_t s) {
     k_greedy<RC, LR><<<grid, BLOCK, 0, s>>>(K);
 }
 
+#ifdef WH_WITH_TPE
+// Thread-per-environment kernels (experimental/wh_tpe.cuh) for the default path of Small / Medium.
+template <int RC>
+static void launch_tpe(Kind kind, const KParams &K, cudaStream_t s) {
+    constexpr int WARPS = 4;
+    const size_t smem = (size_t)WARPS * Tpe<RC>::BYTES;
+    const unsigned grid = (unsigned)((K.N + 32 * WARPS - 1) / (32 * WARPS));
+    if (kind == K_GSTEP) {
+        static const cudaError_t once = cudaFuncSetAttribute(k_step_tpe<RC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        (void)once;
+        k_step_tpe<RC, true><<<grid, 32 * WARPS, smem, s>>>(K);
+    } else {
+        static const cudaError_t once = cudaFuncSetAttribute(k_step_tpe<RC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        (void)once;
+        k_step_tpe<RC, false><<<grid, 32 * WARPS, smem, s>>>(K);
+    }
+}
+
+static bool tpe_enabled() {
+    static const bool on = getenv("WH_ENABLE_TPE") != nullptr;
+    return on;
+}
+#endif
+
 static int launch(Kind kind, const KParams &K, const Shape &sh, void *stream) {
     if (K.N <= 0) return 0;
     if ((unsigned long long)K.N * (K.R * K.R > 2 * K.P ? K.R * K.R : 2 * K.P) >= (1ull << 32)) return WH_E_CONFIG;   // 32-bit in-launch indexing: shard the batch
@@ -340,7 +367,15 @@ static int launch(Kind kind, const KParams &K, const Shape &sh, void *stream) {
         else if (K.R == 9) launch_greedy<9, 3>(K, s);
         else if (K.R == 16) launch_greedy<16, 4>(K, s);
         else launch_greedy<0, 4>(K, s);
-    } else if (sh.RC == 4) launch_kind<4, 4>(kind, K, s);
+    }
+#ifdef WH_WITH_TPE
+    else if ((kind == K_STEP || kind == K_GSTEP) && (sh.RC == 4 || sh.RC == 9) && !K.order && !K.spawn_p &&
+             K.regular_racks && tpe_enabled()) {
+        if (sh.RC == 4) launch_tpe<4>(kind, K, s);
+        else launch_tpe<9>(kind, K, s);
+    }
+#endif
+    else if (sh.RC == 4) launch_kind<4, 4>(kind, K, s);
     else if (sh.RC == 9) launch_kind<9, 9>(kind, K, s);
     else if (sh.RC == 16) launch_kind<16, 16>(kind, K, s);
     else launch_kind<0, 0>(kind, K, s);
