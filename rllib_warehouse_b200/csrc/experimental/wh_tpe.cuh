@@ -1,11 +1,14 @@
 // wh_tpe.cuh — EXPERIMENTAL thread-per-environment step kernel for the small-footprint variants.
 //
 // STATUS (round 1): bit-exact (the whole -m gpu suite passes with it dispatched for Small / Medium)
-// but SLOWER than the lane-group kernels on B200 — Small 0.57 vs 0.68, Medium 0.71 vs 0.86 of the
-// HBM peak: 21 % / 37 % fewer warp instructions, but 80-96 registers and 10-18 KB of staging per
-// warp leave only 24 / 12 resident warps per SM, and the fully unrolled body thrashes the
-// instruction cache (`no_instruction` stalls). Not compiled by default: build with -DWH_WITH_TPE and
-// run with WH_ENABLE_TPE=1 to A/B it. See profiles/README.md.
+// but SLOWER than the lane-group kernels on B200. First version (everything inlined, int4 / int2
+// staging): Small 0.57 vs 0.68, Medium 0.71 vs 0.86 of the HBM peak — 21 % / 37 % fewer warp
+// instructions, but 10.9 k SASS instructions of mostly straight-line code (instruction-cache misses)
+// and 18 KB of staging per warp (12 resident warps per SM for Medium). This version (cold helpers out
+// of line, compact staging tables, 5.1 k SASS): Small 0.63, Medium 0.82; an occupancy sweep
+// (32..114 registers) does not close the gap, the per-thread dependency chains do not hide behind
+// 16-32 warps. Not compiled by default: build with -DWH_WITH_TPE and run with WH_ENABLE_TPE=1 to A/B
+// it. See profiles/README.md.
 //
 // The lane-group kernels (wh_kernels.cuh) give one environment G = R lanes; for Small (R = 4) and
 // Medium (R = 9) they are bound by instruction issue, not by HBM: every warp instruction serves only
@@ -41,8 +44,8 @@ struct Tpe {
     static constexpr int ROW_POS = 2 * R, STR_POS = tpe_odd_words(ROW_POS);
     static constexpr int ROW_TGT = R, STR_TGT = tpe_odd_words(ROW_TGT);
     static constexpr int ROW_REW = 4 * R, STR_REW = tpe_odd_words(ROW_REW);
-    static constexpr int ROW_REQ = 16 * R, STR_REQ = (RC == 4) ? 80 : ROW_REQ;   // 128-bit accesses: Small needs 80, Medium's 144 is free
-    static constexpr int ROW_PP = 8 * R, STR_PP = (RC == 4) ? 40 : ROW_PP;      // 64-bit accesses
+    static constexpr int STR_REQ = tpe_odd_words(4 * R);   // compact request list: 4 bytes (px,py,dx,dy) per request
+    static constexpr int STR_PP = tpe_odd_words(2 * R);    // padded position / target-cell tables: one u16 cell per row
     static constexpr int ROW_SA = R, STR_SA = tpe_odd_words(ROW_SA);
     static constexpr int ROW_OA = R * (R - 1), STR_OA = tpe_odd_words(ROW_OA);
     __host__ __device__ static constexpr int al16(int v) { return (v + 15) / 16 * 16; }
@@ -70,6 +73,20 @@ template <> struct TpeVec<4> { typedef int32_t type; };
 template <> struct TpeVec<2> { typedef int16_t type; };
 template <> struct TpeVec<1> { typedef int8_t type; };
 
+// cold helpers are kept out of line so that the hot body stays small (instruction cache)
+__device__ __noinline__ uint2 tpe_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, unsigned long long seed) {
+    uint32_t a, b;
+    philox4x32_10(c0, c1, c2, c3, seed, a, b);
+    return make_uint2(a, b);
+}
+
+// regular racks only (4, 8, 12, ...): the dispatcher guarantees it
+__device__ __forceinline__ int tpe_pickup_index(int L, int x, int y) {
+    const int qx = (x + 1) >> 2, ox = (x + 1) & 3, qy = (y + 1) >> 2, oy = (y + 1) & 3;
+    const bool ok = ox < 2 && oy < 2 && qx >= 1 && qx <= L && qy >= 1 && qy <= L;
+    return ok ? 4 * ((qx - 1) * L + (qy - 1)) + ox + 2 * oy : -1;
+}
+
 // Streams the rows of `nl` consecutive environments (ROW bytes each, padded to STRIDE in shared
 // memory) into the contiguous global block that starts at gdst.
 template <int ROW, int STRIDE>
@@ -87,8 +104,14 @@ __device__ __forceinline__ void tpe_flush(void *gdst, const unsigned char *sbase
     }
 }
 
+#ifndef WH_TPE_MB_SMALL
+#define WH_TPE_MB_SMALL 8
+#endif
+#ifndef WH_TPE_MB_MEDIUM
+#define WH_TPE_MB_MEDIUM 4
+#endif
 template <int RC, bool GREEDY>
-__global__ void __launch_bounds__(128) k_step_tpe(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(128, (RC == 4 ? WH_TPE_MB_SMALL : WH_TPE_MB_MEDIUM)) k_step_tpe(const __grid_constant__ KParams P) {
     using T = Tpe<RC>;
     constexpr int R = RC, NP = T::P, PW = T::PW;
     constexpr int PBITS = NP <= 16 ? 16 : (NP <= 32 ? 32 : 64);
@@ -108,7 +131,7 @@ __global__ void __launch_bounds__(128) k_step_tpe(const __grid_constant__ KParam
     // my rows in the per-warp regions
     uint8_t *s_pt = W + T::O_PT + lane * T::STR_PT;             // int8  [P]  pickup targets (dynamic indexing)
     int16_t *s_tm = reinterpret_cast<int16_t *>(W + T::O_TM + lane * T::STR_TM);   // int16 [P] timers
-    int4 *s_req = reinterpret_cast<int4 *>(W + T::O_REQ + lane * T::STR_REQ);       // compact request list
+    uint32_t *s_req = reinterpret_cast<uint32_t *>(W + T::O_REQ + lane * T::STR_REQ);   // compact request list (px,py,dx,dy bytes)
 
     // ------------------------------------------------------------------------------- load state
     int time = P.time[e], A = P.num_agents[e], ep = P.episode_ctr[e];
@@ -139,11 +162,10 @@ __global__ void __launch_bounds__(128) k_step_tpe(const __grid_constant__ KParam
             if ((((pw[p >> 2] >> (8 * (p & 3) + 7)) & 1u) == 0u) && rank < R) s_idx[rank++] = (uint8_t)p;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            int4 q = make_int4(P.null_pos, P.null_pos, P.null_pos, P.null_pos);   // only if < R active (unreachable)
+            uint32_t q = null16 | (null16 << 16);                              // only if < R active (unreachable)
             if (r < rank) {
                 const int p = s_idx[r];
-                const uint32_t pc = pickup_cell16(P, p), dc = delivery_cell16((int)(s_pt[p] & 0x3Fu), dim);
-                q = make_int4(pc & 0xFF, pc >> 8, dc & 0xFF, dc >> 8);
+                q = pickup_cell16(P, p) | (delivery_cell16((int)(s_pt[p] & 0x3Fu), dim) << 16);
             }
             s_req[r] = q;
         }
@@ -157,7 +179,7 @@ __global__ void __launch_bounds__(128) k_step_tpe(const __grid_constant__ KParam
         scan_requests(ptw);
         uint32_t cells[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) { const int4 q = s_req[r]; cells[r] = (uint32_t)q.x | ((uint32_t)q.y << 8); }
+        for (int r = 0; r < R; ++r) cells[r] = s_req[r] & 0xFFFFu;
 #pragma unroll
         for (int a = 0; a < R; ++a) {
             const int px = pos16[a] & 0xFF, py = pos16[a] >> 8;
@@ -174,7 +196,7 @@ __global__ void __launch_bounds__(128) k_step_tpe(const __grid_constant__ KParam
             int action = (sx + 1) * 3 + (sy + 1);                              // solvers.py:41,47-49
             if (P.rand_thr) {                                                  // solvers.py:44-45
                 uint32_t u0, u1;
-                philox4x32_10(env_id, (uint32_t)ep, (uint32_t)time, (uint32_t)a, P.solver_seed, u0, u1);
+                { const uint2 ph_ = tpe_philox(env_id, (uint32_t)ep, (uint32_t)time, (uint32_t)a, P.solver_seed); u0 = ph_.x; u1 = ph_.y; }
                 if ((unsigned long long)u0 < P.rand_thr) action = (int)bounded(u1, 9u);
             }
             act[a] = (a < A) ? action : -1;
@@ -252,7 +274,7 @@ __global__ void __launch_bounds__(128) k_step_tpe(const __grid_constant__ KParam
 #pragma unroll
         for (int a = 0; a < R; ++a) {
             reward[a] = 0.0f;
-            cand[a] = (a < A) ? pickup_index(P, pos16[a] & 0xFF, pos16[a] >> 8) : -1;
+            cand[a] = (a < A) ? tpe_pickup_index(P.L, pos16[a] & 0xFF, pos16[a] >> 8) : -1;
             tgv[a] = (cand[a] >= 0) ? (int)(int8_t)s_pt[cand[a]] : -1;        // pre-assignment targets (core.py:320-324)
         }
 #pragma unroll
@@ -281,7 +303,7 @@ __global__ void __launch_bounds__(128) k_step_tpe(const __grid_constant__ KParam
             const int n_inact = __popcll(inactive);
             for (int i = 0; i < k; ++i) {
                 uint32_t up, ut;
-                philox4x32_10(env_id, (uint32_t)ep, (uint32_t)time, (uint32_t)i, P.seed, up, ut);
+                { const uint2 ph_ = tpe_philox(env_id, (uint32_t)ep, (uint32_t)time, (uint32_t)i, P.seed); up = ph_.x; ut = ph_.y; }
                 const int p = nth_set64<PBITS>(inactive, (int)bounded(up, (uint32_t)(n_inact - i)));
                 const int d = nth_set64<64>(avail_d, (int)bounded(ut, (uint32_t)(P.D - i)));
                 inactive &= ~(1ull << p);
@@ -345,7 +367,7 @@ __global__ void __launch_bounds__(128) k_step_tpe(const __grid_constant__ KParam
         time = 0;
         uint32_t u0, u1;
         if (P.random_agents) {                                                 // variants.py:70,74
-            philox4x32_10(env_id, (uint32_t)ep, CTR_NUM_AGENTS, 0u, P.seed, u0, u1);
+            { const uint2 ph_ = tpe_philox(env_id, (uint32_t)ep, CTR_NUM_AGENTS, 0u, P.seed); u0 = ph_.x; u1 = ph_.y; }
             A = 1 + (int)bounded(u0, (uint32_t)P.max_agents);
         }
 #pragma unroll
@@ -355,9 +377,9 @@ __global__ void __launch_bounds__(128) k_step_tpe(const __grid_constant__ KParam
             pos16[a] = 0xFFFFu;
             if (a < A) {
                 for (uint32_t j = 0;; ++j) {                                   // core.py:192-201
-                    philox4x32_10(env_id, (uint32_t)ep, CTR_SPAWN_AGENT + j, (uint32_t)a, P.seed, u0, u1);
+                    { const uint2 ph_ = tpe_philox(env_id, (uint32_t)ep, CTR_SPAWN_AGENT + j, (uint32_t)a, P.seed); u0 = ph_.x; u1 = ph_.y; }
                     const int x = 1 + (int)bounded(u0, (uint32_t)(dim - 2)), y = 1 + (int)bounded(u1, (uint32_t)(dim - 2));
-                    if (pickup_index(P, x, y) < 0) { pos16[a] = (uint32_t)x | ((uint32_t)y << 8); break; }
+                    if (tpe_pickup_index(P.L, x, y) < 0) { pos16[a] = (uint32_t)x | ((uint32_t)y << 8); break; }
                 }
             }
         }
@@ -368,7 +390,7 @@ __global__ void __launch_bounds__(128) k_step_tpe(const __grid_constant__ KParam
         unsigned long long inactive = (NP >= 64) ? ~0ull : ((1ull << NP) - 1ull);
         unsigned long long avail_d = (P.D >= 64) ? ~0ull : ((1ull << P.D) - 1ull);
         for (int i = 0; i < R; ++i) {                                          // core.py:215-221
-            philox4x32_10(env_id, (uint32_t)ep, CTR_INIT_REQUESTS, (uint32_t)i, P.seed, u0, u1);
+            { const uint2 ph_ = tpe_philox(env_id, (uint32_t)ep, CTR_INIT_REQUESTS, (uint32_t)i, P.seed); u0 = ph_.x; u1 = ph_.y; }
             const int p = nth_set64<PBITS>(inactive, (int)bounded(u0, (uint32_t)(NP - i)));
             const int d = nth_set64<64>(avail_d, (int)bounded(u1, (uint32_t)(P.D - i)));
             inactive &= ~(1ull << p);
@@ -384,8 +406,8 @@ __global__ void __launch_bounds__(128) k_step_tpe(const __grid_constant__ KParam
     const bool want_obs = P.obs.requests != nullptr;
     if (want_obs) {
         scan_requests(ptw);                                     // s_pt mirrors ptw at this point
-        int2 *s_pp = reinterpret_cast<int2 *>(W + T::O_PP + lane * T::STR_PP);
-        int2 *s_tp = reinterpret_cast<int2 *>(W + T::O_TP + lane * T::STR_PP);
+        uint16_t *s_pp = reinterpret_cast<uint16_t *>(W + T::O_PP + lane * T::STR_PP);
+        uint16_t *s_tp = reinterpret_cast<uint16_t *>(W + T::O_TP + lane * T::STR_PP);
         int8_t *s_sa = reinterpret_cast<int8_t *>(W + T::O_SA + lane * T::STR_SA);
         uint32_t avail_bits = 0;
 #pragma unroll
@@ -396,8 +418,8 @@ __global__ void __launch_bounds__(128) k_step_tpe(const __grid_constant__ KParam
             const uint32_t tp = (flavour == WH_OBS_STEP && delivering) ? tcell[r] : null16;
             const int av = (flavour == WH_OBS_STEP && real && !delivering) ? 1 : 0;
             avail_bits |= (uint32_t)av << r;
-            s_pp[r] = make_int2(pp & 0xFF, pp >> 8);
-            s_tp[r] = make_int2(tp & 0xFF, tp >> 8);
+            s_pp[r] = (uint16_t)pp;
+            s_tp[r] = (uint16_t)tp;
             s_sa[r] = (int8_t)av;
         }
         int8_t *s_oa = reinterpret_cast<int8_t *>(W + T::O_OA + lane * T::STR_OA);
@@ -437,8 +459,16 @@ __global__ void __launch_bounds__(128) k_step_tpe(const __grid_constant__ KParam
     // ------------------------------------------------------------------------------- flush: observations
     const wh_obs &o = P.obs;
     const size_t row0 = (size_t)e0 * R;
-    tpe_flush<T::ROW_PP, T::STR_PP>(o.self_position + row0 * 2, W + T::O_PP, nl, lane);
-    tpe_flush<T::ROW_PP, T::STR_PP>(o.self_delivery_target + row0 * 2, W + T::O_TP, nl, lane);
+    {   // self_position / self_delivery_target [env][r] = padded table rows, expanded to int32 pairs
+        int2 *dsp = reinterpret_cast<int2 *>(o.self_position) + row0, *dst = reinterpret_cast<int2 *>(o.self_delivery_target) + row0;
+        for (unsigned i = lane; i < (unsigned)nl * R; i += 32) {
+            const unsigned el = i / (unsigned)R, r = i - el * R;
+            const uint32_t pc = reinterpret_cast<const uint16_t *>(W + T::O_PP + el * T::STR_PP)[r];
+            const uint32_t tc = reinterpret_cast<const uint16_t *>(W + T::O_TP + el * T::STR_PP)[r];
+            dsp[i] = make_int2(pc & 0xFF, pc >> 8);
+            dst[i] = make_int2(tc & 0xFF, tc >> 8);
+        }
+    }
     tpe_flush<T::ROW_SA, T::STR_SA>(o.self_availability + row0, W + T::O_SA, nl, lane);
     tpe_flush<T::ROW_OA, T::STR_OA>(o.other_availabilities + row0 * (R - 1), W + T::O_OA, nl, lane);
     {   // num_agents key: A replicated over the R rows of an env
@@ -451,7 +481,8 @@ __global__ void __launch_bounds__(128) k_step_tpe(const __grid_constant__ KParam
         const unsigned total = (unsigned)nl * R * R;
         for (unsigned i = lane; i < total; i += 32) {
             const unsigned el = i / (unsigned)(R * R), rem = i - el * (R * R), r = rem % (unsigned)R;
-            dst[i] = *reinterpret_cast<const int4 *>(W + T::O_REQ + el * T::STR_REQ + r * 16);
+            const uint32_t q = reinterpret_cast<const uint32_t *>(W + T::O_REQ + el * T::STR_REQ)[r];
+            dst[i] = make_int4(q & 0xFF, (q >> 8) & 0xFF, (q >> 16) & 0xFF, q >> 24);
         }
     }
     {   // other_positions / other_delivery_targets [env][a][o] = padded row o + (o >= dropped row); 2 rows per int4
@@ -465,16 +496,15 @@ __global__ void __launch_bounds__(128) k_step_tpe(const __grid_constant__ KParam
             const unsigned f0 = 2 * k, f1 = 2 * k + 1;
             const unsigned a0 = f0 / (unsigned)(R - 1), o0 = f0 - a0 * (R - 1);
             const unsigned a1 = f1 / (unsigned)(R - 1), o1 = f1 - a1 * (R - 1);
-            const unsigned char *pp = W + T::O_PP + el * T::STR_PP, *tp = W + T::O_TP + el * T::STR_PP;
-            const int2 p0 = reinterpret_cast<const int2 *>(pp)[o0 + (o0 >= a0 ? 1 : 0)];
-            const int2 p1 = reinterpret_cast<const int2 *>(pp)[o1 + (o1 >= a1 ? 1 : 0)];
-            dpos[i] = make_int4(p0.x, p0.y, p1.x, p1.y);                       // core.py:426
+            const uint16_t *pp = reinterpret_cast<const uint16_t *>(W + T::O_PP + el * T::STR_PP);
+            const uint16_t *tp = reinterpret_cast<const uint16_t *>(W + T::O_TP + el * T::STR_PP);
+            const uint32_t p0 = pp[o0 + (o0 >= a0 ? 1 : 0)], p1 = pp[o1 + (o1 >= a1 ? 1 : 0)];
+            dpos[i] = make_int4(p0 & 0xFF, p0 >> 8, p1 & 0xFF, p1 >> 8);       // core.py:426
             // core.py:428: step() always drops row 1; a reset observation drops row a (core.py:256)
             const bool rst = auto_reset && sdone[el] != 0;
             const unsigned d0 = rst ? a0 : 1u, d1 = rst ? a1 : 1u;
-            const int2 t0 = reinterpret_cast<const int2 *>(tp)[o0 + (o0 >= d0 ? 1 : 0)];
-            const int2 t1 = reinterpret_cast<const int2 *>(tp)[o1 + (o1 >= d1 ? 1 : 0)];
-            dtgt[i] = make_int4(t0.x, t0.y, t1.x, t1.y);
+            const uint32_t t0 = tp[o0 + (o0 >= d0 ? 1 : 0)], t1 = tp[o1 + (o1 >= d1 ? 1 : 0)];
+            dtgt[i] = make_int4(t0 & 0xFF, t0 >> 8, t1 & 0xFF, t1 >> 8);
         }
     }
 }
