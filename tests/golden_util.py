@@ -122,3 +122,56 @@ def check_solver(greedy_fn, d):
                     pad(d["random_actions"], -1))
     assert np.array_equal(_np(got)[:, :A].astype(np.int64), d["actions"].astype(np.int64))
     return n
+
+
+# ---- full-size reference digests (oracle/make_golden_batch.py) --------------------------------
+def _crc(a, dtype):
+    import zlib
+    return zlib.crc32(np.ascontiguousarray(_np(a), dtype=dtype).tobytes())
+
+
+def batch_actions(d):
+    """The action tensor [T, N, A] of a `random` batch, regenerated from its recorded PCG64 seed
+    (guarded by a CRC so that a changed numpy stream is reported as such, not as a parity bug)."""
+    T, n, A = int(d["T"]), int(d["n"]), int(d["A"])
+    acts = np.random.Generator(np.random.PCG64(int(d["seed_actions"]))).integers(0, 9, size=(T, n, A)).astype(np.int32)
+    assert _crc(acts, np.int32) == int(d["actions_crc_all"]), "numpy PCG64 integers() stream changed"
+    return acts
+
+
+def check_batch_digests(make_env, d, greedy_fn=None, steps=None):
+    """Replays a whole recorded reference batch (all N envs at once, T steps) on an env-like object
+    and compares, at every step, the CRC-32 of every full [N, ...] output array — state, all
+    observation keys, actions, rewards, dones — with what the UNMODIFIED reference produced.
+    greedy_fn(env) -> actions [N, R] for `greedy` batches (the solver under test)."""
+    n, A, R = int(d["n"]), int(d["A"]), int(d["R"])
+    T = int(d["T"]) if steps is None else steps
+    policy = str(d["policy"])
+    env = make_env(cfg_kwargs(d), n, A)
+    obs = env.reset(agent_pos=d["reset_agent_pos"], init_pickups=d["reset_init_pickups"],
+                    init_targets=d["reset_init_targets"], num_agents=np.full(n, A, np.int32))
+
+    def outputs(obs):
+        out = dict(get_state(env))
+        out.update({"obs_" + k: obs[k] for k in OBS_KEYS})
+        return out
+
+    got = outputs(obs)
+    for k, want in zip(d["reset_keys"], d["reset_crc"]):
+        assert _crc(got[str(k)], np.int32) == int(want), f"reset: '{k}' differs from the reference"
+    acts_all = batch_actions(d) if policy == "random" else None
+    keys = [str(k) for k in d["out_keys"]]
+    ret = np.zeros(n, np.float64)
+    for t in range(T):
+        acts = _np(greedy_fn(env))[:, :A].astype(np.int32) if policy == "greedy" else acts_all[t]
+        obs, rew, dones = env.step(acts, spawn_pickups=d["spawn_pickups"][t], spawn_targets=d["spawn_targets"][t])
+        got = outputs(obs)
+        got.update(actions=acts, rewards=_np(rew)[:, :A], dones=_np(dones))
+        for j, k in enumerate(keys):
+            dt = np.float32 if k == "rewards" else (np.uint8 if k == "dones" else np.int32)
+            assert _crc(got[k], dt) == int(d["step_crc"][t, j]), f"step {t}: '{k}' differs from the reference"
+        ret += _np(rew)[:, :A].sum(axis=1)
+    if T == int(d["T"]):
+        assert_state(env, {k: d["final_" + k] for k in STATE_KEYS}, "final state")
+        assert np.array_equal(ret.astype(np.float32), d["return_per_env"])
+    return n * T

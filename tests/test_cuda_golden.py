@@ -41,3 +41,14 @@ def test_quirk_scenarios():
 @pytest.mark.parametrize("size", gu.SIZES)
 def test_solver(size):
     assert gu.check_solver(greedy_fn, gu.load(f"solver_{size}.npz")) == 120
+
+
+@pytest.mark.parametrize("name", ["small_random", "medium_greedy", "large_random"])
+def test_full_size_reference_digests(name):
+    """BASELINE configs[1] exactly as SURVEY §8d config 2 states it — 4 096 Small envs, 200 steps,
+    env e = the unmodified reference seeded with BASE+e, PCG64 action tensor — plus the Medium
+    greedy-solver and Large replay subsets: every state tensor, observation key, action, reward and
+    done flag of the CUDA path has the reference's CRC at every step."""
+    d = gu.load(f"batch_{name}.npz")
+    n = gu.check_batch_digests(make_env, d, greedy_fn=lambda env: env.greedy_actions().clone())
+    assert n == int(d["n"]) * 200

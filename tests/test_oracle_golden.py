@@ -57,3 +57,12 @@ def test_solver(size):
     pure = greedy_fn(gu.cfg_kwargs(d), {k: d["obs_" + k] for k in gu.OBS_KEYS},
                      np.full(120, d["actions"].shape[1], np.int32), 0.0, None, None)
     assert np.array_equal(pure[:, : d["actions"].shape[1]][keep], d["actions"][keep])
+
+
+@pytest.mark.parametrize("name", ["small_random", "medium_greedy", "large_random"])
+def test_full_size_reference_digests(name):
+    """BASELINE configs[1] at full size (4 096 Small envs x 200 steps) and the configs[2]/[3] replay
+    subsets: the C oracle reproduces the reference's per-step CRCs of every output array."""
+    d = gu.load(f"batch_{name}.npz")
+    n = gu.check_batch_digests(make_env, d, greedy_fn=lambda env: env.greedy().copy())
+    assert n == int(d["n"]) * 200
