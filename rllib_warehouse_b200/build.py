@@ -30,20 +30,22 @@ def up_to_date():
     return all(os.path.getmtime(os.path.join(CSRC, d)) <= t for d in DEPS)
 
 
-def build(force=False, verbose=False):
-    if not force and up_to_date():
+def build(force=False, verbose=False, extra_flags=(), out=None):
+    """extra_flags / out: kernel-tuning builds (tools/ab_build.py) next to the default library."""
+    if out is None and not force and up_to_date():
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", LIB, *SOURCES]
+    out = out or LIB
+    cmd = [nvcc_path(), *NVCC_FLAGS, *extra_flags, "-o", out, *SOURCES]
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     log = res.stdout + res.stderr
-    with open(os.path.join(LIB_DIR, "build.log"), "w") as f:
+    with open(os.path.join(LIB_DIR, "build.log") if out == LIB else out + ".log", "w") as f:
         f.write(" ".join(cmd) + "\n" + log)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + log[-4000:])
     if verbose:
         print(log)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

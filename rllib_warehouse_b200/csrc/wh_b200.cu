@@ -32,6 +32,9 @@ namespace wh {
 #ifndef WH_MIN_BLOCKS_SMALL
 #define WH_MIN_BLOCKS_SMALL 6
 #endif
+#ifndef WH_LARGE_DYN_SMEM
+#define WH_LARGE_DYN_SMEM 24576   // 34.5 KB static + 24 KB: 3 blocks fit in 227 KB, 4 do not
+#endif
 constexpr int BLOCK = WH_BLOCK;   // threads per block (tuning: -DWH_BLOCK / -DWH_MIN_BLOCKS)
 
 // ---------------------------------------------------------------------------------------------
@@ -163,7 +166,7 @@ __global__ void __launch_bounds__(BLOCK) k_obs(const __grid_constant__ KParams P
     EnvRegs s;
     load_env(P, g, t.e, R, (RC ? 4 * GC : P.P), s);
     const unsigned long long active = active_mask(g, s.pt4);
-    build_obs<GC, RC>(P, g, t.e, R, s, active, target_cell16(P, s.atgt), P.flavour, t.live, StageMem<GC, RC>::mine(smem, g));
+    build_obs<GC, RC>(P, g, t.e, R, s, active, target_cell16<GC>(P, s.atgt), P.flavour, t.live, StageMem<GC, RC>::mine(smem, g));
 }
 
 // RLlib-flattened float32 observations from the resident state
@@ -176,7 +179,7 @@ __global__ void __launch_bounds__(BLOCK) k_obs_flat(const __grid_constant__ KPar
     EnvRegs s;
     load_env(P, g, t.e, R, (RC ? 4 * GC : P.P), s);
     const unsigned long long active = active_mask(g, s.pt4);
-    build_obs_flat<GC, RC>(P, g, t.e, R, s, active, target_cell16(P, s.atgt), P.flavour, t.live,
+    build_obs_flat<GC, RC>(P, g, t.e, R, s, active, target_cell16<GC>(P, s.atgt), P.flavour, t.live,
                            P.flat_out, reinterpret_cast<float *>(StageMem<GC, RC, true>::mine(smem, g)));
 }
 
@@ -286,10 +289,13 @@ static int fill_params(const wh_config *cfg, KParams &K, Shape &sh) {
     K.G = G;
     K.invL = (256 + K.L - 1) / K.L;
     sh.G = G; sh.RC = 0;
-    // compile-time-shaped kernels need R == G and P == 4G (every lane owns one agent and 4 points)
-    if (K.R == 4 && G == 4 && K.P == 16) sh.RC = 4;        // WarehouseSmall
-    if (K.R == 9 && G == 9 && K.P == 36) sh.RC = 9;        // WarehouseMedium: 3 envs per warp
-    if (K.R == 16 && G == 16 && K.P == 64) sh.RC = 16;     // WarehouseLarge
+    // compile-time-shaped kernels: exactly the reference variants' geometry (R == G, P == 4G, their
+    // area dimension and regular racks 4,8,12,..; see Geo<GC>); anything else runs the runtime kernels
+    if (K.regular_racks) {
+        if (K.R == 4 && K.L == 2 && K.dim == 12) sh.RC = 4;        // WarehouseSmall  (variants.py:25-32)
+        if (K.R == 9 && K.L == 3 && K.dim == 16) sh.RC = 9;        // WarehouseMedium (variants.py:40-47): 3 envs per warp
+        if (K.R == 16 && K.L == 4 && K.dim == 20) sh.RC = 16;      // WarehouseLarge  (variants.py:55-62)
+    }
     return 0;
 }
 
@@ -316,9 +322,18 @@ static void launch_kind(Kind kind, const KParams &K, cudaStream_t s) {
     const int G = GC ? GC : K.G;
     const long long epw = 32 / G, warps = (K.N + epw - 1) / epw;
     const unsigned grid = (unsigned)((warps * 32 + BLOCK - 1) / BLOCK);
+    // unused dynamic shared memory caps the resident blocks per SM where fewer, fatter warps measured
+    // faster than what the register count alone would allow (Large: 3 blocks, profiles/README.md)
+    const size_t dyn = RC == 16 ? WH_LARGE_DYN_SMEM : 0;
+    if (dyn) {   // static + dynamic > 48 KB needs the opt-in
+        static const cudaError_t once[2] = {
+            cudaFuncSetAttribute(k_step<GC, RC, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn),
+            cudaFuncSetAttribute(k_step<GC, RC, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)};
+        (void)once;
+    }
     switch (kind) {
-    case K_STEP: k_step<GC, RC, false, false><<<grid, BLOCK, 0, s>>>(K); break;
-    case K_GSTEP: k_step<GC, RC, true, false><<<grid, BLOCK, 0, s>>>(K); break;
+    case K_STEP: k_step<GC, RC, false, false><<<grid, BLOCK, dyn, s>>>(K); break;
+    case K_GSTEP: k_step<GC, RC, true, false><<<grid, BLOCK, dyn, s>>>(K); break;
     case K_STEP_FLAT: k_step<GC, RC, false, true><<<grid, BLOCK, 0, s>>>(K); break;
     case K_RESET: k_reset<GC, RC><<<grid, BLOCK, 0, s>>>(K); break;
     case K_OBS: k_obs<GC, RC><<<grid, BLOCK, 0, s>>>(K); break;

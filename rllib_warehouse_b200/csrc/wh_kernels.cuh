@@ -129,6 +129,31 @@ __device__ __forceinline__ int nth_set_small(uint32_t m, int r) {
     return __ffs((int)m) - 1;
 }
 
+// Geometry as the kernels see it. The variant kernels (GC = 4 / 9 / 16, launched only for exactly
+// WarehouseSmall / Medium / Large: variants.py:25-32,40-47,55-62) get every value as a compile-time
+// constant (no parameter loads, folded arithmetic, no irregular-rack code); GC = 0 reads KParams.
+#ifndef WH_GEO_CONST_LARGE
+#define WH_GEO_CONST_LARGE 1
+#endif
+template <int GC>
+struct Geo {
+    int dim, L, PP, D, null_pos, invL;
+    bool regular;
+    __device__ __forceinline__ explicit Geo(const KParams &P) {
+        constexpr bool FIXED = GC == 4 || GC == 9 || (GC == 16 && WH_GEO_CONST_LARGE);
+        if (GC == 4) { dim = 12; L = 2; }
+        else if (GC == 9) { dim = 16; L = 3; }
+        else if (FIXED) { dim = 20; L = 4; }
+        else { dim = P.dim; L = P.L; }
+        PP = FIXED ? 4 * L * L : P.P;
+        D = FIXED ? 4 * (dim - 4) : P.D;
+        null_pos = FIXED ? dim / 2 : P.null_pos;                               // core.py:107
+        invL = FIXED ? (256 + L - 1) / L : P.invL;
+        regular = FIXED ? true : (P.regular_racks != 0);
+    }
+    __device__ __forceinline__ uint32_t null16() const { return (uint32_t)null_pos | ((uint32_t)null_pos << 8); }
+};
+
 // core.py:178-188  delivery point d -> cell, v = 2 + d/4, side = d%4: (v,0) (0,v) (v,dim-1) (dim-1,v)
 __device__ __forceinline__ uint32_t delivery_cell16(int d, int dim) {
     // sides 0,2 (even): x = v, y = 0 | dim-1      sides 1,3 (odd): x = 0 | dim-1, y = v
@@ -141,28 +166,30 @@ __device__ __forceinline__ uint32_t delivery_cell16(int d, int dim) {
 
 // core.py:171-175  pickup point p -> cell: racks[p/(4L)], racks[(p/4)%L], corner p%4 in
 // (-1,-1) (0,-1) (-1,0) (0,0)
-__device__ __forceinline__ uint32_t pickup_cell16(const KParams &P, int p) {
+template <int GC>
+__device__ __forceinline__ uint32_t pickup_cell16(const KParams &P, const Geo<GC> &geo, int p) {
     const int q = p >> 2, c = p & 3;
-    const int rxi = (q * P.invL) >> 8, ryi = q - rxi * P.L;
-    const int rx = P.regular_racks ? 4 * (rxi + 1) : P.racks[rxi];
-    const int ry = P.regular_racks ? 4 * (ryi + 1) : P.racks[ryi];
+    const int rxi = (q * geo.invL) >> 8, ryi = q - rxi * geo.L;
+    const int rx = geo.regular ? 4 * (rxi + 1) : P.racks[rxi];
+    const int ry = geo.regular ? 4 * (ryi + 1) : P.racks[ryi];
     return (uint32_t)(rx - 1 + (c & 1)) | ((uint32_t)(ry - 1 + (c >> 1)) << 8);
 }
 
 // inverse of pickup_cell16: FIRST pickup index at cell (x,y) or -1 (core.py:319 argmax = first match)
-__device__ __forceinline__ int pickup_index(const KParams &P, int x, int y) {
-    if (P.regular_racks) {  // racks = 4,8,12,... (all reference variants)
+template <int GC>
+__device__ __forceinline__ int pickup_index(const KParams &P, const Geo<GC> &geo, int x, int y) {
+    if (geo.regular) {  // racks = 4,8,12,... (all reference variants)
         const int qx = (x + 1) >> 2, ox = (x + 1) & 3, qy = (y + 1) >> 2, oy = (y + 1) & 3;
-        const bool ok = ox < 2 && oy < 2 && qx >= 1 && qx <= P.L && qy >= 1 && qy <= P.L;
-        return ok ? 4 * ((qx - 1) * P.L + (qy - 1)) + ox + 2 * oy : -1;
+        const bool ok = ox < 2 && oy < 2 && qx >= 1 && qx <= geo.L && qy >= 1 && qy <= geo.L;
+        return ok ? 4 * ((qx - 1) * geo.L + (qy - 1)) + ox + 2 * oy : -1;
     }
     int ix = -1, iy = -1, ox = 0, oy = 0;
-    for (int i = P.L - 1; i >= 0; --i) {  // descending so that the smallest matching index wins
+    for (int i = geo.L - 1; i >= 0; --i) {  // descending so that the smallest matching index wins
         const int r = P.racks[i];
         if (x == r - 1 || x == r) { ix = i; ox = (x == r); }
         if (y == r - 1 || y == r) { iy = i; oy = (y == r); }
     }
-    return (ix >= 0 && iy >= 0) ? 4 * (ix * P.L + iy) + ox + 2 * oy : -1;
+    return (ix >= 0 && iy >= 0) ? 4 * (ix * geo.L + iy) + ox + 2 * oy : -1;
 }
 
 // A group of G consecutive lanes. GC = compile-time G (0 => runtime G from the launch parameters).
@@ -189,6 +216,23 @@ struct Group {
     }
     __device__ __forceinline__ uint32_t ballot(bool p) const {
         return (__ballot_sync(FULL, p) & gmask) >> gshift;
+    }
+    // does any lane of my group have `hit` set? hit = (mark == c) | (armed & (mm in {rev, ca, cb})):
+    // one predicate chain (4 ISETP + 1 PLOP3) feeding the vote instead of 0/1 integers and SELs
+    __device__ __forceinline__ bool any_hit(uint32_t mm, uint32_t mark, uint32_t c, uint32_t rev, uint32_t ca,
+                                            uint32_t cb, uint32_t armed) const {
+        uint32_t b;
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\t"
+            "setp.eq.u32 p, %1, %2;\n\t"
+            "setp.eq.or.u32 p, %3, %2, p;\n\t"
+            "setp.eq.or.u32 p, %4, %2, p;\n\t"
+            "setp.ne.u32 q, %5, 0;\n\t"
+            "and.pred p, p, q;\n\t"
+            "setp.eq.or.u32 p, %6, %7, p;\n\t"
+            "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t}"
+            : "=r"(b) : "r"(rev), "r"(mm), "r"(ca), "r"(cb), "r"(armed), "r"(mark), "r"(c));
+        return (b & gmask) != 0u;
     }
     __device__ __forceinline__ uint32_t shfl(uint32_t v, int src) const {
         return __shfl_sync(FULL, v, gshift + src);
@@ -328,13 +372,14 @@ __device__ __forceinline__ unsigned long long active_mask(const Group<GC> &g, ui
 template <int GC, int RC>
 __device__ __forceinline__ void do_moves(const KParams &P, const Group<GC> &g, int R, int A,
                                          int act, int ord, bool have_order, uint32_t &pos16) {
+    const Geo<GC> geo(P);
     const int px = pos16 & 0xFF, py = pos16 >> 8;
     uint32_t m = ABSENT_MOVE, rev = ABSENT_MOVE, ca = ABSENT_MOVE, cb = ABSENT_MOVE;
     if (g.gl < A && act >= 0 && act <= 8) {
         const int ax = (act * 11) >> 5;            // act / 3 for 0..8   (MOVES, core.py:38)
         int x = px + ax - 1, y = py + (act - 3 * ax) - 1;
-        if ((unsigned)x >= (unsigned)P.dim) x = px;  // per-axis clamp => wall sliding (core.py:284-287)
-        if ((unsigned)y >= (unsigned)P.dim) y = py;
+        if ((unsigned)x >= (unsigned)geo.dim) x = px;  // per-axis clamp => wall sliding (core.py:284-287)
+        if ((unsigned)y >= (unsigned)geo.dim) y = py;
         const uint32_t to = (uint32_t)x | ((uint32_t)y << 8);
         m = pos16 | (to << 16);
         rev = to | (pos16 << 16);                                              // core.py:294
@@ -346,7 +391,7 @@ __device__ __forceinline__ void do_moves(const KParams &P, const Group<GC> &g, i
         }
     }
     uint32_t mark = (g.gl < A) ? pos16 : NO_CELL;   // core.py:276: every agent marks its cell
-    bool moved = false;   // arms rev / ca / cb (an ABSENT move is rejected below whatever `hit` says)
+    uint32_t moved = 0u;  // arms rev / ca / cb (an ABSENT move is rejected below whatever `hit` says)
     int n_order = R;
     if (have_order) {  // entries after the first -1 are ignored
         const uint32_t neg = g.ballot(g.gl < R && ord < 0);
@@ -361,20 +406,18 @@ __device__ __forceinline__ void do_moves(const KParams &P, const Group<GC> &g, i
             uint32_t mm = g.shfl(m, cur < 0 ? 0 : cur);
             if (cur < 0) mm = ABSENT_MOVE;
             const uint32_t c = mm >> 16, from = mm & 0xFFFFu;
-            const bool hit = (mark == c) | (moved & ((rev == mm) | (ca == mm) | (cb == mm)));
-            const bool ok = (g.ballot(hit) == 0u) && (mm != ABSENT_MOVE);      // core.py:289
+            const bool ok = !g.any_hit(mm, mark, c, rev, ca, cb, moved) && (mm != ABSENT_MOVE);   // core.py:289
             if (ok && mark == from) mark = NO_CELL;                            // core.py:290
-            if (ok && g.gl == cur) { mark = c; moved = true; }                 // core.py:291-297
+            if (ok && g.gl == cur) { mark = c; moved = 1u; }                   // core.py:291-297
         }
     } else {
 #pragma unroll
         for (int t = 0; t < RR; ++t) {                                         // ascending agent ids
             const uint32_t mm = g.shfl(m, t);
             const uint32_t c = mm >> 16, from = mm & 0xFFFFu;
-            const bool hit = (mark == c) | (moved & ((rev == mm) | (ca == mm) | (cb == mm)));
-            const bool ok = (g.ballot(hit) == 0u) && (mm != ABSENT_MOVE);      // core.py:289
+            const bool ok = !g.any_hit(mm, mark, c, rev, ca, cb, moved) && (mm != ABSENT_MOVE);   // core.py:289
             if (ok && mark == from) mark = NO_CELL;                            // core.py:290
-            if (ok && g.gl == t) { mark = c; moved = true; }                   // core.py:291-297
+            if (ok && g.gl == t) { mark = c; moved = 1u; }                     // core.py:291-297
         }
     }
     if (moved) pos16 = m >> 16;                                                // core.py:299-300
@@ -394,6 +437,7 @@ template <int GC>
 __device__ __forceinline__ StepOut do_world(const KParams &P, const Group<GC> &g, env_t e, int R,
                                             uint32_t env_id, EnvRegs &s, bool replay) {
     StepOut o;
+    const Geo<GC> geo(P);
     // ---- core.py:303-306 expiry (before pickup detection) ----
     int nexp = 0;
 #pragma unroll
@@ -405,7 +449,7 @@ __device__ __forceinline__ StepOut do_world(const KParams &P, const Group<GC> &g
     o.nexp = __any_sync(FULL, nexp != 0) ? g.add(nexp) : 0;
     // ---- core.py:309-335 pickups: agent on a pickup cell, free, request waiting there ----
     const int x = s.pos16 & 0xFF, y = s.pos16 >> 8;
-    const int cand = (g.gl < s.A) ? pickup_index(P, x, y) : -1;
+    const int cand = (g.gl < s.A) ? pickup_index(P, geo, x, y) : -1;
     const uint32_t w = g.shfl(s.pt4, (cand < 0 ? 0 : cand) >> 2);
     const int tg = (int)(int8_t)((w >> (8 * (cand & 3))) & 0xFFu);
     const bool picks = cand >= 0 && s.atgt == -1 && tg > -1;
@@ -434,9 +478,9 @@ __device__ __forceinline__ StepOut do_world(const KParams &P, const Group<GC> &g
     }
     if (__any_sync(FULL, k > 0)) {
         if (!replay) philox4x32_10(env_id, (uint32_t)s.ep, (uint32_t)s.time, (uint32_t)g.gl, P.seed, up, ut);
-        const unsigned long long pmask = (P.P >= 64) ? ~0ull : ((1ull << P.P) - 1ull);
+        const unsigned long long pmask = (geo.PP >= 64) ? ~0ull : ((1ull << geo.PP) - 1ull);
         unsigned long long inactive = ~active & pmask;
-        unsigned long long avail_d = (P.D >= 64) ? ~0ull : ((1ull << P.D) - 1ull);
+        unsigned long long avail_d = (geo.D >= 64) ? ~0ull : ((1ull << geo.D) - 1ull);
         const int n_inact = __popcll(inactive);
         for (int i = 0; __any_sync(FULL, i < k); ++i) {
             int p, d;
@@ -445,7 +489,7 @@ __device__ __forceinline__ StepOut do_world(const KParams &P, const Group<GC> &g
                 d = (int)g.shfl((uint32_t)st_, i);
             } else {
                 const uint32_t a = g.shfl(up, i), b = g.shfl(ut, i);
-                const int ni = n_inact - i, di = P.D - i;
+                const int ni = n_inact - i, di = geo.D - i;
                 p = nth_set64<Group<GC>::PBITS>(inactive, (int)bounded(a, (uint32_t)(ni > 0 ? ni : 1)));
                 d = nth_set64<64>(avail_d, (int)bounded(b, (uint32_t)(di > 0 ? di : 1)));
             }
@@ -463,11 +507,10 @@ __device__ __forceinline__ StepOut do_world(const KParams &P, const Group<GC> &g
         }
     }
     // ---- core.py:354-368 deliveries (an agent that picked up THIS step is already delivering) ----
-    const uint32_t null16 = (uint32_t)P.null_pos | ((uint32_t)P.null_pos << 8);
-    o.tpos16 = null16;
+    o.tpos16 = geo.null16();
     bool delivered = false;
     if (g.gl < s.A && s.atgt > -1) {
-        const uint32_t dcell = delivery_cell16(s.atgt, P.dim);
+        const uint32_t dcell = delivery_cell16(s.atgt, geo.dim);
         delivered = dcell == s.pos16;
         if (delivered) { s.atgt = -1; reward += 1.0f; }
         else o.tpos16 = dcell;
@@ -500,8 +543,9 @@ template <int GC, int RC>
 __device__ __forceinline__ void build_obs(const KParams &P, const Group<GC> &g, env_t e, int R,
                                           const EnvRegs &s, unsigned long long active, uint32_t tpos16,
                                           int flavour, bool live, unsigned char *stage) {
-    const int null_pos = P.null_pos;
-    const uint32_t null16 = (uint32_t)null_pos | ((uint32_t)null_pos << 8);
+    const Geo<GC> geo(P);
+    const int null_pos = geo.null_pos;
+    const uint32_t null16 = geo.null16();
     const bool real = g.gl < s.A;
     const bool delivering = real && s.atgt > -1;
     // core.py:372-407 padded tables (reset flavour: availability 0 and null targets, core.py:233-236)
@@ -523,8 +567,8 @@ __device__ __forceinline__ void build_obs(const KParams &P, const Group<GC> &g, 
     const uint32_t w4 = g.shfl(s.pt4, p >> 2);
     int4 rq = make_int4(null_pos, null_pos, null_pos, null_pos);  // only if < R active (unreachable)
     if (have) {
-        const uint32_t pc = pickup_cell16(P, p);
-        const uint32_t dc = delivery_cell16((int)((w4 >> (8 * (p & 3))) & 0x3Fu), P.dim);
+        const uint32_t pc = pickup_cell16(P, geo, p);
+        const uint32_t dc = delivery_cell16((int)((w4 >> (8 * (p & 3))) & 0x3Fu), geo.dim);
         rq = make_int4(pc & 0xFF, pc >> 8, dc & 0xFF, dc >> 8);
     }
 
@@ -640,8 +684,9 @@ template <int GC, int RC>
 __device__ __forceinline__ void build_obs_flat(const KParams &P, const Group<GC> &g, env_t e, int R,
                                                const EnvRegs &s, unsigned long long active, uint32_t tpos16,
                                                int flavour, bool live, float *out, float *stage) {
-    const int null_pos = P.null_pos;
-    const uint32_t null16 = (uint32_t)null_pos | ((uint32_t)null_pos << 8);
+    const Geo<GC> geo(P);
+    const int null_pos = geo.null_pos;
+    const uint32_t null16 = geo.null16();
     const bool real = g.gl < s.A;
     const bool delivering = real && s.atgt > -1;
     const uint32_t ppos = real ? s.pos16 : null16;
@@ -656,8 +701,8 @@ __device__ __forceinline__ void build_obs_flat(const KParams &P, const Group<GC>
     const uint32_t w4 = g.shfl(s.pt4, p >> 2);
     float4 rq = make_float4((float)null_pos, (float)null_pos, (float)null_pos, (float)null_pos);
     if (have) {
-        const uint32_t pc = pickup_cell16(P, p);
-        const uint32_t dc = delivery_cell16((int)((w4 >> (8 * (p & 3))) & 0x3Fu), P.dim);
+        const uint32_t pc = pickup_cell16(P, geo, p);
+        const uint32_t dc = delivery_cell16((int)((w4 >> (8 * (p & 3))) & 0x3Fu), geo.dim);
         rq = make_float4((float)(pc & 0xFF), (float)(pc >> 8), (float)(dc & 0xFF), (float)(dc >> 8));
     }
     const int F = 9 * R + 1;
@@ -717,8 +762,10 @@ __device__ __forceinline__ void build_obs_flat(const KParams &P, const Group<GC>
 }
 
 // delivery-target cell of my agent for the observation tables (null cell when not delivering)
+template <int GC>
 __device__ __forceinline__ uint32_t target_cell16(const KParams &P, int atgt) {
-    return atgt > -1 ? delivery_cell16(atgt, P.dim) : ((uint32_t)P.null_pos | ((uint32_t)P.null_pos << 8));
+    const Geo<GC> geo(P);
+    return atgt > -1 ? delivery_cell16(atgt, geo.dim) : geo.null16();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -729,6 +776,7 @@ __device__ __forceinline__ unsigned long long do_reset(const KParams &P, const G
                                                        int R, uint32_t env_id, EnvRegs &s, bool replay,
                                                        bool doit) {
     // `doit` is uniform within the group; groups that skip still take part in warp-wide votes
+    const Geo<GC> geo(P);
     EnvRegs n = s;
     n.ep = s.ep + 1;
     n.time = 0;                                                                // core.py:168
@@ -750,9 +798,9 @@ __device__ __forceinline__ unsigned long long do_reset(const KParams &P, const G
         for (uint32_t j = 0; __any_sync(FULL, need); ++j) {
             if (need) {
                 philox4x32_10(env_id, (uint32_t)n.ep, CTR_SPAWN_AGENT + j, (uint32_t)g.gl, P.seed, u0, u1);
-                const int x = 1 + (int)bounded(u0, (uint32_t)(P.dim - 2));
-                const int y = 1 + (int)bounded(u1, (uint32_t)(P.dim - 2));
-                if (pickup_index(P, x, y) < 0) { n.pos16 = (uint32_t)x | ((uint32_t)y << 8); need = false; }
+                const int x = 1 + (int)bounded(u0, (uint32_t)(geo.dim - 2));
+                const int y = 1 + (int)bounded(u1, (uint32_t)(geo.dim - 2));
+                if (pickup_index(P, geo, x, y) < 0) { n.pos16 = (uint32_t)x | ((uint32_t)y << 8); need = false; }
             }
         }
     }
@@ -765,8 +813,8 @@ __device__ __forceinline__ unsigned long long do_reset(const KParams &P, const G
     } else {
         philox4x32_10(env_id, (uint32_t)n.ep, CTR_INIT_REQUESTS, (uint32_t)g.gl, P.seed, u0, u1);
     }
-    unsigned long long inactive = (P.P >= 64) ? ~0ull : ((1ull << P.P) - 1ull);
-    unsigned long long avail_d = (P.D >= 64) ? ~0ull : ((1ull << P.D) - 1ull);
+    unsigned long long inactive = (geo.PP >= 64) ? ~0ull : ((1ull << geo.PP) - 1ull);
+    unsigned long long avail_d = (geo.D >= 64) ? ~0ull : ((1ull << geo.D) - 1ull);
     unsigned long long active = 0ull;
     for (int i = 0; i < R; ++i) {
         int p, d;
@@ -775,8 +823,8 @@ __device__ __forceinline__ unsigned long long do_reset(const KParams &P, const G
             d = (int)g.shfl((uint32_t)st_, i);
         } else {
             const uint32_t a = g.shfl(u0, i), b = g.shfl(u1, i);
-            p = nth_set64<Group<GC>::PBITS>(inactive, (int)bounded(a, (uint32_t)(P.P - i)));
-            d = nth_set64<64>(avail_d, (int)bounded(b, (uint32_t)(P.D - i)));
+            p = nth_set64<Group<GC>::PBITS>(inactive, (int)bounded(a, (uint32_t)(geo.PP - i)));
+            d = nth_set64<64>(avail_d, (int)bounded(b, (uint32_t)(geo.D - i)));
         }
         if (p >= 0) {
             inactive &= ~(1ull << p);
@@ -805,12 +853,13 @@ __device__ __forceinline__ unsigned long long do_reset(const KParams &P, const G
 template <int GC, int RC>
 __device__ __forceinline__ int greedy_from_state(const KParams &P, const Group<GC> &g, int R,
                                                  uint32_t env_id, const EnvRegs &s) {
+    const Geo<GC> geo(P);
     const unsigned long long active = active_mask(g, s.pt4);
     const int px = s.pos16 & 0xFF, py = s.pos16 >> 8;
     // lane r takes the r-th active pickup point's cell
     const int nact = __popcll(active);
-    uint32_t cell = (uint32_t)P.null_pos | ((uint32_t)P.null_pos << 8);
-    if (g.gl < nact && g.gl < R) cell = pickup_cell16(P, nth_set64<Group<GC>::PBITS>(active, g.gl));
+    uint32_t cell = geo.null16();
+    if (g.gl < nact && g.gl < R) cell = pickup_cell16(P, geo, nth_set64<Group<GC>::PBITS>(active, g.gl));
     int best = 1 << 30;
     uint32_t bcell = 0;
     const int RR = RC ? RC : R;
@@ -823,8 +872,8 @@ __device__ __forceinline__ int greedy_from_state(const KParams &P, const Group<G
     uint32_t target;
     const bool free_agent = s.time > 0 && s.atgt == -1;                        // availability 1
     if (free_agent) target = bcell;
-    else if (s.time > 0) target = delivery_cell16(s.atgt, P.dim);              // solvers.py:33-34
-    else target = (uint32_t)P.null_pos | ((uint32_t)P.null_pos << 8);
+    else if (s.time > 0) target = delivery_cell16(s.atgt, geo.dim);              // solvers.py:33-34
+    else target = geo.null16();
     const int sx = max(-1, min(1, (int)(target & 0xFF) - px));                 // solvers.py:41
     const int sy = max(-1, min(1, (int)(target >> 8) - py));
     int action = (sx + 1) * 3 + (sy + 1);                                      // solvers.py:47-49
