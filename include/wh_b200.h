@@ -86,6 +86,10 @@ typedef struct wh_obs {
 #define WH_FLAG_COMPACT_IO 2   /* wh_step: `actions` points to int8 [N,R] and `rewards` to uint8 [N,R]
                                   (values 0/1/2) instead of int32 / float32 — 4x less PCIe traffic for
                                   host-driven loops; semantics unchanged */
+#define WH_FLAG_NO_PDL 4       /* launch this step without programmatic stream serialization. By default
+                                  the step kernels let the NEXT step launch on the same stream be scheduled
+                                  while they drain (it touches no memory before they complete); callers
+                                  that put copies between the launches gain nothing from it */
 
 /* stats vector (unsigned 64-bit counters, device memory, WH_NUM_STATS entries):
  * [0] episodes [1] return_sum [2] pickups [3] deliveries [4] expired [5..7] reserved

@@ -11,6 +11,7 @@ NUM_STATS = 80
 OBS_STEP, OBS_RESET = 0, 1
 FLAG_AUTO_RESET = 1
 FLAG_COMPACT_IO = 2
+FLAG_NO_PDL = 4
 
 OBS_KEYS = (
     "num_agents", "self_position", "self_availability", "self_delivery_target",

@@ -339,7 +339,7 @@ static void launch_step(void (*kern)(const KParams), unsigned grid, size_t dyn, 
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cfg.numAttrs = (pdl_enabled() && !(K.flags & WH_FLAG_NO_PDL)) ? 1 : 0;
     cudaLaunchKernelEx(&cfg, kern, K);
 }
 
@@ -690,19 +690,19 @@ static int env_step_impl(wh_env *E, const int32_t *actions, float *rewards, uint
         if (greedy) {
             rc = wh_greedy_step(&E->cfg, &st, n, E->env_id0 + e0, E->seed, E->seed ^ 0x5EEDull, 0, nullptr,
                                 E->d_rewards + e0 * R, E->d_dones + e0, E->d_stats, &ob,
-                                WH_FLAG_AUTO_RESET, s);
+                                WH_FLAG_AUTO_RESET | WH_FLAG_NO_PDL, s);
         } else {
             if (compact) {
                 int8_t *da = reinterpret_cast<int8_t *>(E->d_actions) + e0 * R;
                 CK(cudaMemcpyAsync(da, reinterpret_cast<const int8_t *>(actions) + e0 * R, n * R, cudaMemcpyHostToDevice, s));
                 rc = wh_step(&E->cfg, &st, n, E->env_id0 + e0, E->seed, reinterpret_cast<const int32_t *>(da), nullptr,
                              nullptr, nullptr, reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(E->d_rewards) + e0 * R),
-                             E->d_dones + e0, E->d_stats, &ob, WH_FLAG_AUTO_RESET | WH_FLAG_COMPACT_IO, s);
+                             E->d_dones + e0, E->d_stats, &ob, WH_FLAG_AUTO_RESET | WH_FLAG_COMPACT_IO | WH_FLAG_NO_PDL, s);
             } else {
                 CK(cudaMemcpyAsync(E->d_actions + e0 * R, actions + e0 * R, n * R * 4, cudaMemcpyHostToDevice, s));
                 rc = wh_step(&E->cfg, &st, n, E->env_id0 + e0, E->seed, E->d_actions + e0 * R, nullptr, nullptr,
                              nullptr, E->d_rewards + e0 * R, E->d_dones + e0, E->d_stats, &ob,
-                             WH_FLAG_AUTO_RESET, s);
+                             WH_FLAG_AUTO_RESET | WH_FLAG_NO_PDL, s);
             }
         }
         E->launches += 1;
