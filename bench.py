@@ -504,6 +504,32 @@ def extras(args, dev, peak):
                                          "frac": ALG_BYTES_PER_ENV_STEP["small"] * 4096 / ms_graph / 1e6 / peak,
                                          "note": "50 steps per graph replay; the whole working set fits in L2"},
     }
+    # BASELINE configs[0]: ONE Small env driven exactly like baseline/run.py:20-62 — the reference-named
+    # dict API (WarehouseSmall(4), WarehouseRandomGreedySolver p=0), one 200-step episode. Per step: one
+    # H2D + launch + D2H for the solver and the same for the env (packed pinned buffers), dict building
+    # in Python. The reference's own single-core Python step + solver for this case: ~385 us.
+    try:
+        from rllib_warehouse_b200 import WarehouseRandomGreedySolver, WarehouseSmall
+        wenv = WarehouseSmall(4)
+        solver = WarehouseRandomGreedySolver(wenv.num_agents, wenv.num_requests, 0.0, wenv.action_space)
+        think = step = 0.0
+        for ep in range(3):                     # episode 0 = warm-up
+            obs, done, n_steps = wenv.reset(), False, 0
+            think = step = 0.0
+            while not done:
+                t0 = time.perf_counter()
+                acts = solver.compute_action(obs)
+                t1 = time.perf_counter()
+                obs, rew, dones, _ = wenv.step(acts)
+                t2 = time.perf_counter()
+                think, step, n_steps, done = think + t1 - t0, step + t2 - t1, n_steps + 1, dones["__all__"]
+        res["configs0_small_single_env_dict_api"] = {
+            "steps": n_steps, "us_per_env_step": 1e6 * step / n_steps, "us_per_solver_call": 1e6 * think / n_steps,
+            "agent_steps_per_sec": 4 * n_steps / (think + step),
+            "note": "reference plumbing check, not a throughput path: 1 env, 4 agents, per-agent dicts on the host",
+        }
+    except Exception as e:  # noqa: BLE001
+        res["configs0_small_single_env_dict_api"] = {"error": repr(e)}
     return res
 
 

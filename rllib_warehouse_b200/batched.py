@@ -31,6 +31,44 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+class Arena:
+    """Several tensors as views into ONE device allocation (every view 256-byte aligned) with a pinned
+    host twin of the same layout, so that a host-driven caller moves all of them with a single copy
+    (the per-env dict API of `core.Warehouse` / `solvers.WarehouseRandomGreedySolver`: one D2H per
+    step instead of one per observation key)."""
+
+    def __init__(self, specs, device):
+        self.offsets, total = {}, 0
+        for name, shape, dtype in specs:
+            total = (total + 255) // 256 * 256
+            nbytes = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+            self.offsets[name] = (total, nbytes, shape, dtype)
+            total += nbytes
+        self.dev = torch.zeros(max(total, 256), dtype=torch.uint8, device=device)
+        self.views = {k: self.dev[o:o + n].view(dt).view(sh) for k, (o, n, sh, dt) in self.offsets.items()}
+        self._host = None
+        self.host_views = None
+
+    def host(self):
+        if self._host is None:
+            self._host = torch.zeros(self.dev.shape, dtype=torch.uint8).pin_memory()
+            self.host_views = {k: self._host[o:o + n].view(dt).view(sh).numpy()
+                               for k, (o, n, sh, dt) in self.offsets.items()}
+        return self._host
+
+    def to_host(self):
+        """device -> pinned host, one copy; returns numpy views (valid until the next call)."""
+        h = self.host()
+        h.copy_(self.dev, non_blocking=True)
+        torch.cuda.current_stream(self.dev.device).synchronize()
+        return self.host_views
+
+    def to_device(self):
+        """pinned host (filled through `host_views`) -> device, one asynchronous copy."""
+        self.dev.copy_(self.host(), non_blocking=True)
+        return self.views
+
+
 class BatchedWarehouse:
     """Structure-of-arrays state + observation tensors for `num_envs` environments on one GPU.
 
@@ -66,18 +104,16 @@ class BatchedWarehouse:
             acc=torch.zeros((N, 4), dtype=torch.int32, device=dev),
         )
         i32, i8 = torch.int32, torch.int8
-        self.obs = dict(
-            num_agents=torch.zeros((N, R, 1), dtype=i32, device=dev),
-            self_position=torch.zeros((N, R, 2), dtype=i32, device=dev),
-            self_availability=torch.zeros((N, R, 1), dtype=i8, device=dev),
-            self_delivery_target=torch.zeros((N, R, 2), dtype=i32, device=dev),
-            other_positions=torch.zeros((N, R, R - 1, 2), dtype=i32, device=dev),
-            other_availabilities=torch.zeros((N, R, R - 1), dtype=i8, device=dev),
-            other_delivery_targets=torch.zeros((N, R, R - 1, 2), dtype=i32, device=dev),
-            requests=torch.zeros((N, R, R, 4), dtype=i32, device=dev),
-        )
-        self.rewards = torch.zeros((N, R), dtype=torch.float32, device=dev)
-        self.dones = torch.zeros(N, dtype=torch.uint8, device=dev)
+        # everything a step returns lives in one arena: `outputs_to_host()` is a single D2H copy
+        self._out = Arena([
+            ("num_agents", (N, R, 1), i32), ("self_position", (N, R, 2), i32),
+            ("self_availability", (N, R, 1), i8), ("self_delivery_target", (N, R, 2), i32),
+            ("other_positions", (N, R, R - 1, 2), i32), ("other_availabilities", (N, R, R - 1), i8),
+            ("other_delivery_targets", (N, R, R - 1, 2), i32), ("requests", (N, R, R, 4), i32),
+            ("rewards", (N, R), torch.float32), ("dones", (N,), torch.uint8)], dev)
+        self.obs = {k: self._out.views[k] for k in OBS_KEYS}
+        self.rewards = self._out.views["rewards"]
+        self.dones = self._out.views["dones"]
         self.actions = torch.full((N, R), -1, dtype=torch.int32, device=dev)
         self.stats = torch.zeros(nv.NUM_STATS, dtype=torch.int64, device=dev)
         self._st = nv.State(**{k: self.state[k].data_ptr() for k in nv.STATE_KEYS})
@@ -87,6 +123,11 @@ class BatchedWarehouse:
     # ------------------------------------------------------------------------------------------
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
+
+    def outputs_to_host(self):
+        """All observation keys + rewards + dones of the last reset/step as numpy views of ONE pinned
+        host buffer, filled by a single device->host copy (meant for small N: the per-env dict API)."""
+        return self._out.to_host()
 
     def obs_bytes_per_env(self):
         return sum(t[0].numel() * t.element_size() for t in self.obs.values())

@@ -11,9 +11,10 @@ device->host copy per step and is NOT the throughput path (that is `BatchedWareh
 from typing import Dict, List, Tuple
 
 import numpy as np
+import torch
 
 from . import spaces
-from .batched import OBS_KEYS, BatchedWarehouse
+from .batched import OBS_KEYS, Arena, BatchedWarehouse
 from .config import WarehouseConfig
 
 try:  # pragma: no cover - ray is absent in the build image
@@ -52,6 +53,10 @@ class Warehouse(MultiAgentEnv):
             seed = int(np.random.randint(0, 2**31 - 1)) | (int(np.random.randint(0, 2**31 - 1)) << 31)
         self._batched = BatchedWarehouse(self._config, 1, num_agents=num_agents,
                                          device=device or _DEFAULT_DEVICE, seed=seed)
+        # actions + dict order travel in one pinned buffer / one H2D copy per step
+        self._in = Arena([("actions", (1, num_requests), torch.int32), ("order", (1, num_requests), torch.int32)],
+                         self._batched.device)
+        self._in.host()
         self._num_agents = num_agents
         self._num_requests = num_requests
         # core.py:111-118
@@ -65,10 +70,12 @@ class Warehouse(MultiAgentEnv):
         self._viewer = None
 
     # ------------------------------------------------------------------------------------------
-    def _obs_dicts(self) -> Dict[str, Dict[str, np.ndarray]]:
-        host = {k: self._batched.obs[k][0].cpu().numpy() for k in OBS_KEYS}
+    def _obs_dicts(self, host=None) -> Dict[str, Dict[str, np.ndarray]]:
+        # one device->host copy for all keys; the per-agent arrays are fresh copies, as in the
+        # reference (callers may keep them across steps)
+        host = self._batched.outputs_to_host() if host is None else host
         A = self.num_agents
-        return {str(i): {k: host[k][i] for k in OBS_KEYS} for i in range(A)}
+        return {str(i): {k: host[k][0, i].copy() for k in OBS_KEYS} for i in range(A)}
 
     def reset(self) -> Dict[str, Dict[str, np.ndarray]]:
         """core.py:167-260 (and variants.py:69-71 for random agent counts)."""
@@ -82,8 +89,9 @@ class Warehouse(MultiAgentEnv):
         """core.py:262-442. Moves are resolved sequentially in `action_dict` iteration order
         (core.py:279); agents missing from the dict do not move."""
         R, A = self._num_requests, self.num_agents
-        actions = np.full((1, R), -1, np.int32)
-        order = np.full((1, R), -1, np.int32)
+        actions, order = self._in.host_views["actions"], self._in.host_views["order"]
+        actions.fill(-1)
+        order.fill(-1)
         ascending = True
         for t, (key, action) in enumerate(action_dict.items()):
             idx = int(key)
@@ -94,10 +102,12 @@ class Warehouse(MultiAgentEnv):
             actions[0, idx] = action % 9
             order[0, t] = idx
             ascending &= t == 0 or order[0, t - 1] < idx
-        self._batched.step(actions, order=None if ascending else order)
-        obs = self._obs_dicts()
-        rew = self._batched.rewards[0].cpu().numpy()
-        done = bool(self._batched.dones[0].item())
+        dev_in = self._in.to_device()
+        self._batched.step(dev_in["actions"], order=None if ascending else dev_in["order"])
+        host = self._batched.outputs_to_host()
+        obs = self._obs_dicts(host)
+        rew = host["rewards"][0].copy()
+        done = bool(host["dones"][0])
         rewards = {str(i): rew[i] for i in range(A)}                            # core.py:435 (np.float32)
         dones = {str(i): done for i in range(A)}                                # core.py:438-440
         dones["__all__"] = done

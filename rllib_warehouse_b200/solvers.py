@@ -3,11 +3,13 @@ the batched warp-argmin kernel (`wh_greedy`)."""
 from abc import ABC, abstractmethod
 from typing import Dict
 
+import ctypes as C
+
 import numpy as np
 import torch
 
 from . import _native as nv
-from .batched import OBS_KEYS, BatchedWarehouse
+from .batched import OBS_KEYS, Arena, BatchedWarehouse
 from .config import WarehouseConfig
 
 __all__ = ["WarehouseSolver", "WarehouseRandomGreedySolver", "BatchedGreedySolver"]
@@ -48,23 +50,43 @@ class WarehouseRandomGreedySolver(WarehouseSolver):
         dim = min(dim, 20)
         cfg = WarehouseConfig(num_requests, dim, tuple(4 * (i + 1) for i in range(L)), 200, 200, num_requests)
         self._env = BatchedWarehouse(cfg, 1, num_agents=num_agents, device=device)
-        self._obs = {k: np.zeros(tuple(self._env.obs[k].shape), dtype=np.int32) for k in OBS_KEYS}
+        R = num_requests
+        # the four keys the solver reads (solvers.py:33-39) + the replayed eps-random branch, packed
+        # in one pinned buffer: one H2D copy, one wh_greedy launch, one D2H copy per call
+        self._in = Arena([("self_position", (1, R, 2), torch.int32), ("self_availability", (1, R, 1), torch.int8),
+                          ("self_delivery_target", (1, R, 2), torch.int32), ("requests", (1, R, R, 4), torch.int32),
+                          ("is_random", (1, R), torch.uint8), ("random_actions", (1, R), torch.int32)],
+                         self._env.device)
+        self._in.host()
+        self._ob = nv.Obs(**{k: (self._in.views[k].data_ptr() if k in self._in.views else None) for k in OBS_KEYS})
+        self._out = Arena([("actions", (1, R), torch.int32)], self._env.device)
 
     def compute_action(self, observations: Dict[str, Dict[str, np.ndarray]]) -> Dict[str, np.ndarray]:
-        A, R = self._num_agents, self._num_requests
+        A = self._num_agents
+        h = self._in.host_views
         for i in range(A):
             o = observations[f"{i}"]
-            self._obs["self_position"][0, i] = o["self_position"]
-            self._obs["self_availability"][0, i] = o["self_availability"]
-            self._obs["self_delivery_target"][0, i] = o["self_delivery_target"]
-            self._obs["requests"][0, i] = o["requests"]
+            h["self_position"][0, i] = o["self_position"]
+            h["self_availability"][0, i] = o["self_availability"]
+            h["self_delivery_target"][0, i] = o["self_delivery_target"]
+            h["requests"][0, i] = o["requests"]
         # solvers.py:44-45: one uniform draw per agent per step (even when prob == 0), and the
         # random action comes from the action space's own sampler
-        is_random = np.zeros((1, R), np.uint8)
-        random_actions = np.full((1, R), -1, np.int32)
+        is_random, random_actions = h["is_random"], h["random_actions"]
+        is_random.fill(0)
+        random_actions.fill(-1)
         for i in range(A):
             if np.random.uniform() < self._random_action_prob:
                 is_random[0, i] = 1
                 random_actions[0, i] = int(self._action_space.sample())
-        acts = self._env.greedy_actions(self._obs, 0.0, 0, is_random, random_actions).cpu().numpy()
-        return {f"{i}": acts[0, i] for i in range(A)}
+        env = self._env
+        d = self._in.to_device()
+        with torch.cuda.device(env.device):
+            rc = env.lib.wh_greedy(C.byref(env._cfg), C.byref(self._ob), env.state["num_agents"].data_ptr(),
+                                   None, None, 1, 0, 0, 0, d["is_random"].data_ptr(),
+                                   d["random_actions"].data_ptr(), self._out.views["actions"].data_ptr(),
+                                   env._stream())
+        nv.check(rc, "wh_greedy")
+        env.launches += 1
+        acts = self._out.to_host()["actions"]
+        return {f"{i}": acts[0, i].copy() for i in range(A)}
