@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(128, (RC == 4 ? WH_TPE_MB_SMALL : WH_TPE_MB_ME
             uint32_t q = null16 | (null16 << 16);                              // only if < R active (unreachable)
             if (r < rank) {
                 const int p = s_idx[r];
-                q = pickup_cell16(P, p) | (delivery_cell16((int)(s_pt[p] & 0x3Fu), dim) << 16);
+                q = pickup_cell16(P, Geo<0>(P), p) | (delivery_cell16((int)(s_pt[p] & 0x3Fu), dim) << 16);
             }
             s_req[r] = q;
         }

@@ -351,11 +351,15 @@ static void launch_kind(Kind kind, const KParams &K, cudaStream_t s) {
     // unused dynamic shared memory caps the resident blocks per SM where fewer, fatter warps measured
     // faster than what the register count alone would allow (Large: 3 blocks, profiles/README.md)
     const size_t dyn = RC == 16 ? WH_LARGE_DYN_SMEM : 0;
-    if (dyn) {   // static + dynamic > 48 KB needs the opt-in
-        static const cudaError_t once[2] = {
-            cudaFuncSetAttribute(k_step<GC, RC, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn),
-            cudaFuncSetAttribute(k_step<GC, RC, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)};
-        (void)once;
+    if (dyn) {   // static + dynamic > 48 KB needs the opt-in, once per device (function attributes are per device)
+        static bool done[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 64 && !done[dev]) {
+            cudaFuncSetAttribute(k_step<GC, RC, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+            cudaFuncSetAttribute(k_step<GC, RC, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+            done[dev] = true;
+        }
     }
     switch (kind) {
     case K_STEP: launch_step(k_step<GC, RC, false, false>, grid, dyn, s, K); break;
