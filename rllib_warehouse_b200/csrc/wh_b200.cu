@@ -43,11 +43,12 @@ constexpr int BLOCK = WH_BLOCK;   // threads per block (tuning: -DWH_BLOCK / -DW
 // Which environment a lane works for: warp w of the grid owns envs [w*epw, (w+1)*epw).
 template <int GC>
 struct Tile {
-    env_t e;
+    env_t e, env0;   // this lane's environment; the first environment of the warp
     bool live;
     __device__ __forceinline__ Tile(const KParams &P, const Group<GC> &g) {
         const uint32_t warp = blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5);
-        const uint32_t env = warp * (uint32_t)g.epw + (uint32_t)g.gi, n = (uint32_t)P.N;
+        env0 = warp * (uint32_t)g.epw;
+        const uint32_t env = env0 + (uint32_t)g.gi, n = (uint32_t)P.N;
         live = !g.ghost && env < n;
         e = (env < n) ? env : n - 1;   // dead lanes shadow a valid env so that loads stay in bounds
     }
@@ -64,6 +65,11 @@ struct StageMem {
         if (RC == 0) return nullptr;
         const int slot = (threadIdx.x >> 5) * EPW + (g.ghost ? 0 : g.gi);
         return base + slot * SLOT;
+    }
+    // the whole staging area of this warp (EPW consecutive slots)
+    __device__ static __forceinline__ unsigned char *warp_area(unsigned char *base) {
+        if (RC == 0) return nullptr;
+        return base + (threadIdx.x >> 5) * EPW * SLOT;
     }
 };
 
@@ -138,7 +144,8 @@ __global__ void __launch_bounds__(BLOCK, (RC == 16 ? WH_MIN_BLOCKS_LARGE : RC ==
         build_obs_flat<GC, RC>(P, g, e, R, s, active, tpos16, flavour, t.live, P.flat_out,
                                reinterpret_cast<float *>(StageMem<GC, RC, true>::mine(smem, g)));
     else if (P.obs.requests)
-        build_obs<GC, RC>(P, g, e, R, s, active, tpos16, flavour, t.live, StageMem<GC, RC>::mine(smem, g));
+        build_obs<GC, RC>(P, g, e, R, s, active, tpos16, flavour, t.live, StageMem<GC, RC>::mine(smem, g),
+                          StageMem<GC, RC>::warp_area(smem), t.env0);
 }
 
 // Warehouse.reset — core.py:167-260
@@ -158,7 +165,9 @@ __global__ void __launch_bounds__(BLOCK) k_reset(const __grid_constant__ KParams
         store_env(P, g, e, R, (RC ? 4 * GC : P.P), s, true);
         if (g.gl == 0) reinterpret_cast<int4 *>(P.acc)[e] = make_int4(0, 0, 0, 0);
     }
-    if (P.obs.requests) build_obs<GC, RC>(P, g, e, R, s, active, 0u, WH_OBS_RESET, doit, StageMem<GC, RC>::mine(smem, g));
+    if (P.obs.requests)
+        build_obs<GC, RC>(P, g, e, R, s, active, 0u, WH_OBS_RESET, doit, StageMem<GC, RC>::mine(smem, g),
+                          StageMem<GC, RC>::warp_area(smem), t.env0);
 }
 
 // observation build alone — core.py:224-260 / 371-432
@@ -171,7 +180,8 @@ __global__ void __launch_bounds__(BLOCK) k_obs(const __grid_constant__ KParams P
     EnvRegs s;
     load_env(P, g, t.e, R, (RC ? 4 * GC : P.P), s);
     const unsigned long long active = active_mask(g, s.pt4);
-    build_obs<GC, RC>(P, g, t.e, R, s, active, target_cell16<GC>(P, s.atgt), P.flavour, t.live, StageMem<GC, RC>::mine(smem, g));
+    build_obs<GC, RC>(P, g, t.e, R, s, active, target_cell16<GC>(P, s.atgt), P.flavour, t.live, StageMem<GC, RC>::mine(smem, g),
+                      StageMem<GC, RC>::warp_area(smem), t.env0);
 }
 
 // RLlib-flattened float32 observations from the resident state

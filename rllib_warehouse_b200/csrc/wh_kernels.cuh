@@ -531,18 +531,30 @@ __device__ __forceinline__ StepOut do_world(const KParams &P, const Group<GC> &g
 // registers. other_*: one environment's block of a key is assembled in shared memory and streamed
 // out with 128-bit stores (st.global.cs: written once, never re-read here).
 // Shared-memory staging area of one environment while its observation is written (compile-time R).
+#ifndef WH_COOP_MEDIUM
+#define WH_COOP_MEDIUM 1
+#endif
 template <int RC>
 struct ObsStage {
     static constexpr int ROWS = RC * (RC - 1);          // "other" rows of one env
     static constexpr int POS_BYTES = 8 * ROWS;          // other_positions / other_delivery_targets
     static constexpr int AV_BYTES = ROWS;               // other_availabilities
-    static constexpr int BYTES = RC ? ((POS_BYTES + AV_BYTES + 15) / 16) * 16 : 16;
+    static constexpr int RAW = RC ? ((POS_BYTES + AV_BYTES + 15) / 16) * 16 : 16;
+    // Warp-cooperative copy-out (Medium, see build_obs): the warp's EPW environments are staged back to
+    // back per key — [EPW][R][R-1] int2 | [EPW][R][R-1] int8 | [EPW][R] int4 request rows — so one slot
+    // is 1/EPW of that area.
+    static constexpr bool COOP = RC == 9 && WH_COOP_MEDIUM;
+    static constexpr int REQ_BYTES = 16 * RC;
+    static constexpr int BYTES = COOP ? ((POS_BYTES + AV_BYTES + REQ_BYTES + 15) / 16) * 16 : RAW;
 };
 
 template <int GC, int RC>
 __device__ __forceinline__ void build_obs(const KParams &P, const Group<GC> &g, env_t e, int R,
                                           const EnvRegs &s, unsigned long long active, uint32_t tpos16,
-                                          int flavour, bool live, unsigned char *stage) {
+                                          int flavour, bool live, unsigned char *stage,
+                                          unsigned char *wstage = nullptr, env_t env0 = 0) {
+    // stage: this environment's staging slot; wstage / env0: the warp's whole staging area and its
+    // first environment (used by the warp-cooperative copy-out only)
     const Geo<GC> geo(P);
     const int null_pos = geo.null_pos;
     const uint32_t null16 = geo.null16();
@@ -585,6 +597,92 @@ __device__ __forceinline__ void build_obs(const KParams &P, const Group<GC> &g, 
     const int2 t_fixed = (g.gl >= 1) ? nx_t : my_t;
     const int RR = RC ? RC : R;
 
+    if constexpr (RC != 0 && ObsStage<RC>::COOP) {
+        // Warp-cooperative copy-out (Medium: 3 environments per warp, 144-byte rows). Written group by
+        // group, every store instruction would emit three separate 144-byte runs = 4.5 sectors each,
+        // half of them starting mid-sector: 98 sectors per environment for 84.7 sectors of data, and the
+        // SM->L2 write path (not HBM) bounds the observation build. The three environments of a warp are
+        // consecutive, so each key's block for the warp is ONE contiguous range: stage it in that
+        // order and let all 32 lanes stream it out, 512 contiguous bytes per store instruction.
+        using St = ObsStage<RC>;
+        constexpr int EPW = 32 / GC;
+        constexpr int ROWS4 = St::ROWS / 2;                        // int4 per env of an [R][R-1] int2 block
+        int2 *w_pos = reinterpret_cast<int2 *>(wstage);                                   // [EPW][R][R-1]
+        int8_t *w_av = reinterpret_cast<int8_t *>(wstage + EPW * St::POS_BYTES);          // [EPW][R][R-1]
+        int4 *w_req = reinterpret_cast<int4 *>(wstage + EPW * (St::POS_BYTES + St::AV_BYTES + 8) / 16 * 16);  // [EPW][R]
+        const int gi = g.ghost ? 0 : g.gi;
+        const bool writer = !g.ghost && g.gl < RC - 1;
+        const uint32_t n = (uint32_t)P.N;
+        const int n_live = env0 >= n ? 0 : (int)((n - env0) < (uint32_t)EPW ? (n - env0) : (uint32_t)EPW);   // envs of this tile
+        if (!g.ghost && g.gl < RC) w_req[gi * RC + g.gl] = rq;                              // core.py:409-418
+#pragma unroll
+        for (int a = 0; a < RC; ++a) {
+            if (writer) {
+                const bool sh = g.gl >= a;                                      // core.py:426-427
+                w_pos[gi * St::ROWS + a * (RC - 1) + g.gl] = sh ? nx_p : my_p;
+                w_av[gi * St::ROWS + a * (RC - 1) + g.gl] = (int8_t)(sh ? nx_a : my_a);
+            }
+        }
+        __syncwarp();
+        const int lane = g.lane;
+        {   // requests [N,R,R,4]: R copies of the env's R request rows (core.py:429)
+            constexpr int PER_ENV = RC * RC;                                    // int4 per env
+            const uint32_t base4 = env0 * (uint32_t)PER_ENV;
+            const int mis = (int)(base4 & 1u);                                  // tile starts mid-sector
+            int4 *d = reinterpret_cast<int4 *>(o.requests) + base4;
+            const int total = n_live * PER_ENV;
+#pragma unroll
+            for (int k = 0; k < (EPW * PER_ENV + 1 + 31) / 32; ++k) {
+                const int i = lane + 32 * k - mis;
+                if (i >= 0 && i < total) {
+                    const int env = (i >= PER_ENV) + (i >= 2 * PER_ENV);
+                    const int r = i - RC * ((i * 57) >> 9);                     // i % 9 for i < 256
+                    static_assert(EPW == 3 && RC == 9, "index arithmetic below is written for 3 x 9");
+                    WH_ST(d + i, w_req[env * RC + r]);
+                }
+            }
+        }
+        {   // other_positions [N,R,R-1,2]
+            int4 *d = reinterpret_cast<int4 *>(o.other_positions) + env0 * (uint32_t)ROWS4;
+            const int total = n_live * ROWS4;
+#pragma unroll
+            for (int k = 0; k < (EPW * ROWS4 + 31) / 32; ++k) {
+                const int i = lane + 32 * k;
+                if (i < total) WH_ST(d + i, reinterpret_cast<const int4 *>(w_pos)[i]);
+            }
+        }
+        {   // other_availabilities [N,R,R-1]: 72 bytes per env = 9 int2
+            int2 *d = reinterpret_cast<int2 *>(o.other_availabilities + (size_t)env0 * St::ROWS);
+            if (lane < n_live * (St::ROWS / 8)) WH_ST(d + lane, reinterpret_cast<const int2 *>(w_av)[lane]);
+        }
+        __syncwarp();
+        int4 *d_t = reinterpret_cast<int4 *>(o.other_delivery_targets) + env0 * (uint32_t)ROWS4;
+        if (flavour == WH_OBS_STEP) {
+            // core.py:428: every agent's block is the same (R-1)-row table; 8 rows = 4 int4 per env
+            if (writer) w_pos[gi * (RC - 1) + g.gl] = t_fixed;
+            __syncwarp();
+            const int total = n_live * ROWS4;
+#pragma unroll
+            for (int k = 0; k < (EPW * ROWS4 + 31) / 32; ++k) {
+                const int i = lane + 32 * k;
+                const int env = (i >= ROWS4) + (i >= 2 * ROWS4);
+                static_assert(ROWS4 % 4 == 0, "table period");
+                if (i < total) WH_ST(d_t + i, reinterpret_cast<const int4 *>(w_pos)[env * ((RC - 1) / 2) + (i & 3)]);
+            }
+        } else {
+#pragma unroll
+            for (int a = 0; a < RC; ++a)
+                if (writer) w_pos[gi * St::ROWS + a * (RC - 1) + g.gl] = (g.gl >= a) ? nx_t : my_t;   // core.py:256
+            __syncwarp();
+            const int total = n_live * ROWS4;
+#pragma unroll
+            for (int k = 0; k < (EPW * ROWS4 + 31) / 32; ++k) {
+                const int i = lane + 32 * k;
+                if (i < total) WH_ST(d_t + i, reinterpret_cast<const int4 *>(w_pos)[i]);
+            }
+        }
+        return;
+    }
     if constexpr (RC != 0) {
         // The "other_*" keys have 8-byte / 1-byte rows: written straight from registers they would
         // leave partially filled 32-byte sectors on the SM->L2 path. Stage one environment's
