@@ -612,8 +612,10 @@ __device__ __forceinline__ void build_obs(const KParams &P, const Group<GC> &g, 
         int4 *w_req = reinterpret_cast<int4 *>(wstage + EPW * (St::POS_BYTES + St::AV_BYTES + 8) / 16 * 16);  // [EPW][R]
         const int gi = g.ghost ? 0 : g.gi;
         const bool writer = !g.ghost && g.gl < RC - 1;
-        const uint32_t n = (uint32_t)P.N;
-        const int n_live = env0 >= n ? 0 : (int)((n - env0) < (uint32_t)EPW ? (n - env0) : (uint32_t)EPW);   // envs of this tile
+        // which of the warp's environments are written at all (envs past N, and envs a masked reset
+        // leaves alone, keep their observations): bit k = environment env0 + k
+        const uint32_t lm = __ballot_sync(FULL, live);
+        auto env_live = [&](int env) { return ((lm >> (env * GC)) & 1u) != 0u; };
         if (!g.ghost && g.gl < RC) w_req[gi * RC + g.gl] = rq;                              // core.py:409-418
 #pragma unroll
         for (int a = 0; a < RC; ++a) {
@@ -630,12 +632,11 @@ __device__ __forceinline__ void build_obs(const KParams &P, const Group<GC> &g, 
             const uint32_t base4 = env0 * (uint32_t)PER_ENV;
             const int mis = (int)(base4 & 1u);                                  // tile starts mid-sector
             int4 *d = reinterpret_cast<int4 *>(o.requests) + base4;
-            const int total = n_live * PER_ENV;
 #pragma unroll
             for (int k = 0; k < (EPW * PER_ENV + 1 + 31) / 32; ++k) {
                 const int i = lane + 32 * k - mis;
-                if (i >= 0 && i < total) {
-                    const int env = (i >= PER_ENV) + (i >= 2 * PER_ENV);
+                const int env = (i >= PER_ENV) + (i >= 2 * PER_ENV);
+                if (i >= 0 && i < EPW * PER_ENV && env_live(env)) {
                     const int r = i - RC * ((i * 57) >> 9);                     // i % 9 for i < 256
                     static_assert(EPW == 3 && RC == 9, "index arithmetic below is written for 3 x 9");
                     WH_ST(d + i, w_req[env * RC + r]);
@@ -644,41 +645,44 @@ __device__ __forceinline__ void build_obs(const KParams &P, const Group<GC> &g, 
         }
         {   // other_positions [N,R,R-1,2]
             int4 *d = reinterpret_cast<int4 *>(o.other_positions) + env0 * (uint32_t)ROWS4;
-            const int total = n_live * ROWS4;
 #pragma unroll
             for (int k = 0; k < (EPW * ROWS4 + 31) / 32; ++k) {
                 const int i = lane + 32 * k;
-                if (i < total) WH_ST(d + i, reinterpret_cast<const int4 *>(w_pos)[i]);
+                const int env = (i >= ROWS4) + (i >= 2 * ROWS4);
+                if (i < EPW * ROWS4 && env_live(env)) WH_ST(d + i, reinterpret_cast<const int4 *>(w_pos)[i]);
             }
         }
         {   // other_availabilities [N,R,R-1]: 72 bytes per env = 9 int2
             int2 *d = reinterpret_cast<int2 *>(o.other_availabilities + (size_t)env0 * St::ROWS);
-            if (lane < n_live * (St::ROWS / 8)) WH_ST(d + lane, reinterpret_cast<const int2 *>(w_av)[lane]);
+            const int env = (lane >= St::ROWS / 8) + (lane >= 2 * (St::ROWS / 8));
+            if (lane < EPW * (St::ROWS / 8) && env_live(env)) WH_ST(d + lane, reinterpret_cast<const int2 *>(w_av)[lane]);
         }
         __syncwarp();
         int4 *d_t = reinterpret_cast<int4 *>(o.other_delivery_targets) + env0 * (uint32_t)ROWS4;
-        if (flavour == WH_OBS_STEP) {
+        // the flavour is per environment (an env that was just auto-reset shows its reset observation),
+        // the copy-out is per warp: take the compact path only if the whole warp is in step flavour
+        if (!__any_sync(FULL, flavour != WH_OBS_STEP)) {
             // core.py:428: every agent's block is the same (R-1)-row table; 8 rows = 4 int4 per env
             if (writer) w_pos[gi * (RC - 1) + g.gl] = t_fixed;
             __syncwarp();
-            const int total = n_live * ROWS4;
 #pragma unroll
             for (int k = 0; k < (EPW * ROWS4 + 31) / 32; ++k) {
                 const int i = lane + 32 * k;
                 const int env = (i >= ROWS4) + (i >= 2 * ROWS4);
                 static_assert(ROWS4 % 4 == 0, "table period");
-                if (i < total) WH_ST(d_t + i, reinterpret_cast<const int4 *>(w_pos)[env * ((RC - 1) / 2) + (i & 3)]);
+                if (i < EPW * ROWS4 && env_live(env)) WH_ST(d_t + i, reinterpret_cast<const int4 *>(w_pos)[env * ((RC - 1) / 2) + (i & 3)]);
             }
         } else {
 #pragma unroll
             for (int a = 0; a < RC; ++a)
-                if (writer) w_pos[gi * St::ROWS + a * (RC - 1) + g.gl] = (g.gl >= a) ? nx_t : my_t;   // core.py:256
+                if (writer)                                                     // core.py:428 (step) / :256 (reset)
+                    w_pos[gi * St::ROWS + a * (RC - 1) + g.gl] = (flavour == WH_OBS_STEP) ? t_fixed : ((g.gl >= a) ? nx_t : my_t);
             __syncwarp();
-            const int total = n_live * ROWS4;
 #pragma unroll
             for (int k = 0; k < (EPW * ROWS4 + 31) / 32; ++k) {
                 const int i = lane + 32 * k;
-                if (i < total) WH_ST(d_t + i, reinterpret_cast<const int4 *>(w_pos)[i]);
+                const int env = (i >= ROWS4) + (i >= 2 * ROWS4);
+                if (i < EPW * ROWS4 && env_live(env)) WH_ST(d_t + i, reinterpret_cast<const int4 *>(w_pos)[i]);
             }
         }
         return;

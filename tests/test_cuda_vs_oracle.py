@@ -467,3 +467,49 @@ def test_back_to_back_launches_match_synchronised_ones(size, n):
             if done.any():                      # what WH_FLAG_AUTO_RESET does in-kernel
                 cpu.reset(env_mask=done.astype(np.uint8))
         same_state(fast, cpu, "after 450 back-to-back launches")
+
+
+@pytest.mark.parametrize("size,n", [("small", 1001), ("medium", 1000), ("large", 333)])
+def test_masked_reset_and_desynchronised_episodes(size, n):
+    """Envs of one warp in different episode phases: (1) a masked reset rewrites the observations of
+    exactly the masked envs and leaves their warp neighbours' untouched, (2) afterwards the envs end
+    their episodes at different steps, so warps hold reset-flavour and step-flavour observations side
+    by side in the auto-reset step. State, observations, rewards, dones vs the oracle throughout."""
+    gpu, cpu = pair(size, n, seed=4242, auto_reset=True)
+    gpu.reset(); cpu.reset()
+    rng = np.random.Generator(np.random.PCG64(9))
+    R = cpu.R
+
+    def step_both(t):
+        actions = rng.integers(0, 9, size=(n, R)).astype(np.int32)
+        _, rew, dones = gpu.step(actions)
+        cpu.step(actions)
+        assert np.array_equal(rew.cpu().numpy(), cpu.rewards), f"step {t}: rewards"
+        assert np.array_equal(dones.cpu().numpy(), cpu.dones), f"step {t}: dones"
+        done = cpu.dones.astype(bool)
+        if done.any():
+            masked_reset_cpu(done.astype(np.uint8))          # what WH_FLAG_AUTO_RESET does in-kernel
+        same_state(gpu, cpu, f"step {t}")
+        same_obs(gpu, cpu, f"step {t}")
+
+    def masked_reset_cpu(mask):
+        # the oracle front-end rebuilds EVERY env's observation in reset flavour; only the masked
+        # envs get one, the others keep the observation they had
+        kept = {k: v.copy() for k, v in cpu.obs.items()}
+        cpu.reset(env_mask=mask)
+        for k in cpu.obs:
+            cpu.obs[k][mask == 0] = kept[k][mask == 0]
+
+    for t in range(60):
+        step_both(t)
+    before = {k: v.clone() for k, v in gpu.obs.items()}
+    mask = (rng.random(n) < 0.4).astype(np.uint8)
+    mask[:9] = [1, 0, 0, 0, 1, 0, 1, 1, 0]
+    gpu.reset(env_mask=mask); masked_reset_cpu(mask)
+    keep = torch.from_numpy(mask == 0).cuda()
+    for k in gu.OBS_KEYS:
+        assert torch.equal(gpu.obs[k][keep], before[k][keep]), f"masked reset touched a neighbour's '{k}'"
+    same_state(gpu, cpu, "masked reset"); same_obs(gpu, cpu, "masked reset")
+    for t in range(60, 270):                        # unmasked envs finish at 200, masked ones at 260
+        step_both(t)
+    assert np.array_equal(gpu.stats.cpu().numpy(), cpu.stats)

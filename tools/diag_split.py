@@ -23,5 +23,11 @@ for v in sys.argv[1:] or ["small", "medium", "large"]:
     def fused(): i[0] += 1; env.step(acts[i[0] % 16])
     def noobs(): i[0] += 1; env.step(acts[i[0] % 16], with_obs=False)
     def obs(): env.build_obs()
-    r = dict(variant=v, fused_ms=timeit(fused), step_only_ms=timeit(noobs), obs_only_ms=timeit(obs))
+    def flat(): i[0] += 1; env.step_flat(acts[i[0] % 16])
+    def gfused(): env.greedy_step(want_actions=False)
+    R = env.R
+    flat_bytes = N * (R * 4 * (9 * R + 1) + 4 * R + 4 * R + R + 1 + 2 * (3 * R + 3 * env.P + 5))
+    r = dict(variant=v, fused_ms=timeit(fused), step_only_ms=timeit(noobs), obs_only_ms=timeit(obs),
+             greedy_fused_ms=timeit(gfused), flat_ms=timeit(flat))
+    r["flat_frac_of_6545.6"] = flat_bytes / (r["flat_ms"] * 1e-3) / 1e9 / 6545.6
     print(json.dumps(r))
