@@ -56,7 +56,7 @@ def run_single(env_size, num_agents, random_action_prob, render):
     return total
 
 
-def run_batched(env_size, num_agents, random_action_prob, num_envs):
+def run_batched(env_size, num_agents, random_action_prob, num_envs, rollout_kernel=False):
     import torch
     from rllib_warehouse_b200 import VARIANTS, BatchedWarehouse
     env = BatchedWarehouse(VARIANTS[env_size], num_envs, num_agents=num_agents, seed=int(time.time()))
@@ -65,18 +65,25 @@ def run_batched(env_size, num_agents, random_action_prob, num_envs):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     steps = 0
-    while True:
-        _, rewards, dones = env.greedy_step(random_action_prob=random_action_prob, solver_seed=1)
-        total += rewards.sum(dim=1)
-        steps += 1
-        if bool(dones[0].item()):
-            break
+    if rollout_kernel:
+        # the whole episode in one launch: state in registers, no per-step observations
+        steps = VARIANTS[env_size].episode_duration
+        total = env.greedy_rollout(steps, random_action_prob=random_action_prob, solver_seed=1,
+                                   with_obs=False).sum(dim=1)
+    else:
+        while True:
+            _, rewards, dones = env.greedy_step(random_action_prob=random_action_prob, solver_seed=1)
+            total += rewards.sum(dim=1)
+            steps += 1
+            if bool(dones[0].item()):
+                break
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     print(f"\n=== Done ({steps} steps x {num_envs} envs) ===")
     print(f"Return per env: mean {total.mean().item():.2f} std {total.std().item():.2f}; "
           f"per agent {total.mean().item() / num_agents:.2f}")
-    print(f"{num_envs * num_agents * steps / dt:.3e} agent-steps/s (solver + step + observations)")
+    what = "solver + step, one launch per episode" if rollout_kernel else "solver + step + observations"
+    print(f"{num_envs * num_agents * steps / dt:.3e} agent-steps/s ({what})")
     print("Episode statistics:", env.stats_dict())
 
 
@@ -87,8 +94,10 @@ if __name__ == "__main__":
     ap.add_argument("random_action_prob", type=float, help="probability of a random action [0.0, 1.0]")
     ap.add_argument("-r", "--render", action="store_true", help="render the environment on each step")
     ap.add_argument("--envs", type=int, default=0, help="run N environments at once on the GPU")
+    ap.add_argument("--rollout-kernel", action="store_true",
+                    help="with --envs: the whole episode in one kernel launch (no per-step observations)")
     a = ap.parse_args()
     if a.envs:
-        run_batched(a.env_size, a.num_agents, a.random_action_prob, a.envs)
+        run_batched(a.env_size, a.num_agents, a.random_action_prob, a.envs, a.rollout_kernel)
     else:
         run_single(a.env_size, a.num_agents, a.random_action_prob, a.render)

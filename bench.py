@@ -448,6 +448,7 @@ def extras(args, dev, peak):
         ms_fused = _time_steps(lambda i: env.greedy_step(want_actions=False), steps, warm)
         rnd = torch.randint(0, 9, (n, env.R), dtype=torch.int32, device=dev)
         ms_flat = _time_steps(lambda i: env.step_flat(rnd), steps, warm)
+        ms_roll = _time_steps(lambda i: env.greedy_rollout(50, with_obs=False), 6, 2) / 50
         sb = SOLVER_BYTES_PER_AGENT[variant] * n * A
         fb = ALG_BYTES_PER_ENV_STEP[variant] * n
         res[name] = {
@@ -456,6 +457,10 @@ def extras(args, dev, peak):
             "solver_plus_step": {"ms": ms_loop, "agent_steps_per_sec": n * A / (ms_loop * 1e-3), "launches_per_step": 2},
             "fused_greedy_step": {"ms": ms_fused, "agent_steps_per_sec": n * A / (ms_fused * 1e-3),
                                   "frac": fb / ms_fused / 1e6 / peak, "launches_per_step": 1},
+            # baseline evaluation (run.py --envs N --rollout-kernel): 50 solver+step iterations per launch,
+            # state in registers, NO observations written — a different (lighter) operation than env.step
+            "greedy_rollout_kernel_no_obs": {"ms_per_step": ms_roll, "agent_steps_per_sec": n * A / (ms_roll * 1e-3),
+                                             "steps_per_launch": 50},
             # RLlib-flattened float32 observations from the step kernel: 4(9R+1) B/agent instead of 33R+4
             "step_flat_f32_obs": {"ms": ms_flat, "agent_steps_per_sec": n * A / (ms_flat * 1e-3),
                                   "alg_bytes_per_launch": fb + n * A * (4 * (9 * A + 1) - (33 * A + 4)),

@@ -154,6 +154,14 @@ int wh_greedy_step(const wh_config *cfg, const wh_state *st, int64_t n_envs, int
                    int32_t *actions_out, float *rewards, uint8_t *dones,
                    unsigned long long *stats, const wh_obs *obs, int flags, void *stream);
 
+/* `n_steps` iterations of baseline/run.py:42-62 (greedy solver -> step) in ONE launch, for evaluating
+ * the baseline at scale: the state stays in registers between the steps and no observation is written
+ * (call wh_build_obs afterwards if one is needed). Leaves state, statistics and dones exactly as n_steps
+ * wh_greedy_step launches would; reward_sums [N,R] = each agent's reward summed over these steps. */
+int wh_greedy_rollout(const wh_config *cfg, const wh_state *st, int64_t n_envs, int64_t env_id0,
+                      uint64_t seed, uint64_t solver_seed, uint64_t rand_threshold, int n_steps,
+                      float *reward_sums, uint8_t *dones, unsigned long long *stats, int flags, void *stream);
+
 /* End-of-rollout reduction of the episode statistics over NVLink: in-place ncclAllReduce(sum) of the
  * WH_NUM_STATS uint64 counters on `stream`. `nccl_comm` is a ncclComm_t created by the caller with
  * the NCCL already loaded in the process (the symbol is resolved at run time with dlsym, so the

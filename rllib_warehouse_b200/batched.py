@@ -207,6 +207,25 @@ class BatchedWarehouse:
         self.launches += 1
         return self.obs, self.rewards, self.dones
 
+    def greedy_rollout(self, steps: int, random_action_prob=0.0, solver_seed=0, with_obs=True):
+        """`steps` iterations of the run.py:42-62 loop (greedy solver -> step) in ONE kernel launch: the
+        state stays in registers between the steps and no per-step observation is written. Leaves the
+        state, `dones` and the statistics exactly as `steps` calls of `greedy_step` would; returns the
+        per-agent reward SUMS of these steps [N, R] (also in `self.rewards`). with_obs: rebuild the
+        resident observations from the final state afterwards (one more launch)."""
+        thr = int(float(random_action_prob) * 4294967296.0)
+        flags = nv.FLAG_AUTO_RESET if self.auto_reset else 0
+        with torch.cuda.device(self.device):
+            rc = self.lib.wh_greedy_rollout(C.byref(self._cfg), C.byref(self._st), self.N, self.env_id0,
+                                            self.seed, int(solver_seed), thr, int(steps),
+                                            self.rewards.data_ptr(), self.dones.data_ptr(),
+                                            self.stats.data_ptr(), flags, self._stream())
+        nv.check(rc, "wh_greedy_rollout")
+        self.launches += 1
+        if with_obs:
+            self.build_obs(nv.OBS_STEP)
+        return self.rewards
+
     def build_obs(self, flavour=nv.OBS_STEP):
         with torch.cuda.device(self.device):
             rc = self.lib.wh_build_obs(C.byref(self._cfg), C.byref(self._st), self.N, int(flavour),

@@ -73,6 +73,29 @@ struct StageMem {
     }
 };
 
+// Per-episode event counters (touched only on events) and, when an episode ends, the statistics
+// vector that mirrors scripts/train.py:18-23. `owner` = the one lane of a live env that does it.
+__device__ __forceinline__ void account_episode(const KParams &P, bool owner, env_t e, const StepOut &so,
+                                                const EnvRegs &s, bool done, bool auto_reset) {
+    const bool flush = s.time == P.episode;
+    if (owner && ((so.npick | so.ndeliv | so.nexp) != 0 || flush || (auto_reset && done))) {
+        int4 a = reinterpret_cast<int4 *>(P.acc)[e];
+        a.x += so.npick; a.y += so.ndeliv; a.z += so.nexp;
+        if (P.stats && flush) {                                                // train.py:18-23
+            const unsigned long long ret = (unsigned long long)(a.x + a.y);
+            atomicAdd(P.stats + 0, 1ull);
+            atomicAdd(P.stats + 1, ret);
+            atomicAdd(P.stats + 2, (unsigned long long)a.x);
+            atomicAdd(P.stats + 3, (unsigned long long)a.y);
+            atomicAdd(P.stats + 4, (unsigned long long)a.z);
+            atomicAdd(P.stats + 8 + 2 * (s.A - 1), 1ull);
+            atomicAdd(P.stats + 9 + 2 * (s.A - 1), ret);
+        }
+        if (auto_reset && done) a = make_int4(0, 0, 0, 0);
+        reinterpret_cast<int4 *>(P.acc)[e] = a;
+    }
+}
+
 // Warehouse.step (+ optional in-kernel greedy solver, + optional observation build, + optional
 // auto-reset) — core.py:262-442, solvers.py:27-58
 template <int GC, int RC, bool GREEDY, bool FLAT>
@@ -115,23 +138,7 @@ __global__ void __launch_bounds__(BLOCK, (RC == 16 ? WH_MIN_BLOCKS_LARGE : RC ==
         if (g.gl == 0) P.dones[e] = done ? 1 : 0;
     }
     const bool auto_reset = (P.flags & WH_FLAG_AUTO_RESET) != 0;
-    const bool flush = s.time == P.episode;
-    if (g.gl == 0 && t.live && ((so.npick | so.ndeliv | so.nexp) != 0 || flush || (auto_reset && done))) {
-        int4 a = reinterpret_cast<int4 *>(P.acc)[e];
-        a.x += so.npick; a.y += so.ndeliv; a.z += so.nexp;
-        if (P.stats && flush) {                                                // train.py:18-23
-            const unsigned long long ret = (unsigned long long)(a.x + a.y);
-            atomicAdd(P.stats + 0, 1ull);
-            atomicAdd(P.stats + 1, ret);
-            atomicAdd(P.stats + 2, (unsigned long long)a.x);
-            atomicAdd(P.stats + 3, (unsigned long long)a.y);
-            atomicAdd(P.stats + 4, (unsigned long long)a.z);
-            atomicAdd(P.stats + 8 + 2 * (s.A - 1), 1ull);
-            atomicAdd(P.stats + 9 + 2 * (s.A - 1), ret);
-        }
-        if (auto_reset && done) a = make_int4(0, 0, 0, 0);
-        reinterpret_cast<int4 *>(P.acc)[e] = a;
-    }
+    account_episode(P, g.gl == 0 && t.live, e, so, s, done, auto_reset);
     int flavour = WH_OBS_STEP;
     bool meta = false;
     if (auto_reset && __any_sync(FULL, done)) {
@@ -146,6 +153,39 @@ __global__ void __launch_bounds__(BLOCK, (RC == 16 ? WH_MIN_BLOCKS_LARGE : RC ==
     else if (P.obs.requests)
         build_obs<GC, RC>(P, g, e, R, s, active, tpos16, flavour, t.live, StageMem<GC, RC>::mine(smem, g),
                           StageMem<GC, RC>::warp_area(smem), t.env0);
+}
+
+// baseline/run.py:42-62 for `n_steps` iterations in ONE launch: greedy solver -> step, the state
+// stays in registers between the steps and no observation is materialised (the solver reads the
+// state it would have been shown). Leaves the state, the per-agent reward sums of these steps, the
+// last step's done flags and the episode statistics exactly as n_steps wh_greedy_step launches do.
+template <int GC, int RC>
+__global__ void __launch_bounds__(BLOCK, (RC == 16 ? 4 : WH_MIN_BLOCKS)) k_rollout(const __grid_constant__ KParams P) {
+    const Group<GC> g(P.G);
+    const Tile<GC> t(P, g);
+    const int R = RC ? RC : P.R;
+    const env_t e = t.e;
+    const uint32_t env_id = (uint32_t)P.env_id0 + e;
+    EnvRegs s;
+    load_env(P, g, e, R, (RC ? 4 * GC : P.P), s);
+    const bool auto_reset = (P.flags & WH_FLAG_AUTO_RESET) != 0;
+    float ret = 0.0f;
+    bool done = false;
+    for (int it = 0; it < P.n_steps; ++it) {
+        const int act = greedy_from_state<GC, RC>(P, g, R, env_id, s);
+        s.time += 1;                                                           // core.py:267
+        do_moves<GC, RC>(P, g, R, s.A, act, -1, false, s.pos16);
+        const StepOut so = do_world(P, g, e, R, env_id, s, false);
+        ret += so.reward;
+        done = s.time >= P.episode;                                            // core.py:438
+        account_episode(P, g.gl == 0 && t.live, e, so, s, done, auto_reset);
+        if (auto_reset && __any_sync(FULL, done)) do_reset(P, g, e, R, env_id, s, false, done && t.live);
+    }
+    if (t.live) {
+        store_env(P, g, e, R, (RC ? 4 * GC : P.P), s, true);
+        if (g.gl < R) P.rewards[e * R + g.gl] = ret;
+        if (g.gl == 0) P.dones[e] = done ? 1 : 0;
+    }
 }
 
 // Warehouse.reset — core.py:167-260
@@ -330,7 +370,7 @@ static bool obs_ok(const wh_obs *o) {
            o->other_positions && o->other_availabilities && o->other_delivery_targets && o->requests;
 }
 
-enum Kind { K_STEP, K_GSTEP, K_STEP_FLAT, K_RESET, K_OBS, K_OBS_FLAT, K_GREEDY };
+enum Kind { K_STEP, K_GSTEP, K_STEP_FLAT, K_RESET, K_OBS, K_OBS_FLAT, K_GREEDY, K_ROLLOUT };
 
 // Step kernels are launched back to back, one per env.step, each depending on the one before
 // through the state tensors. Programmatic stream serialization lets the driver schedule step
@@ -378,6 +418,7 @@ static void launch_kind(Kind kind, const KParams &K, cudaStream_t s) {
     case K_RESET: k_reset<GC, RC><<<grid, BLOCK, 0, s>>>(K); break;
     case K_OBS: k_obs<GC, RC><<<grid, BLOCK, 0, s>>>(K); break;
     case K_OBS_FLAT: k_obs_flat<GC, RC><<<grid, BLOCK, 0, s>>>(K); break;
+    case K_ROLLOUT: k_rollout<GC, RC><<<grid, BLOCK, 0, s>>>(K); break;
     default: break;
     }
 }
@@ -524,6 +565,20 @@ int wh_greedy_step(const wh_config *cfg, const wh_state *st, int64_t n_envs, int
     K.rand_thr = rand_threshold; K.actions_out = actions_out;
     K.rewards = rewards; K.dones = dones; K.stats = stats; K.flags = flags;
     return launch(K_GSTEP, K, sh, stream);
+}
+
+int wh_greedy_rollout(const wh_config *cfg, const wh_state *st, int64_t n_envs, int64_t env_id0,
+                      uint64_t seed, uint64_t solver_seed, uint64_t rand_threshold, int n_steps,
+                      float *reward_sums, uint8_t *dones, unsigned long long *stats, int flags, void *stream) {
+    KParams K; Shape sh;
+    if (int rc = fill_params(cfg, K, sh)) return rc;
+    if (n_envs == 0 || n_steps == 0) return 0;
+    if (!state_ok(st) || !reward_sums || !dones || n_steps < 0) return WH_E_ARG;
+    set_state(K, st);
+    K.N = n_envs; K.env_id0 = env_id0; K.seed = seed; K.solver_seed = solver_seed;
+    K.rand_thr = rand_threshold; K.n_steps = n_steps;
+    K.rewards = reward_sums; K.dones = dones; K.stats = stats; K.flags = flags;
+    return launch(K_ROLLOUT, K, sh, stream);
 }
 
 int wh_build_obs(const wh_config *cfg, const wh_state *st, int64_t n_envs, int flavour,

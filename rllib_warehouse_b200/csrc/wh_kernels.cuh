@@ -76,6 +76,7 @@ struct KParams {
     long long N, env_id0;
     unsigned long long seed, solver_seed, rand_thr;
     int flags, flavour;
+    int n_steps;        // k_rollout: steps per launch
 };
 
 // ---------------------------------------------------------------------------------------------

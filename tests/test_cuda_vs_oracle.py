@@ -513,3 +513,43 @@ def test_masked_reset_and_desynchronised_episodes(size, n):
     for t in range(60, 270):                        # unmasked envs finish at 200, masked ones at 260
         step_both(t)
     assert np.array_equal(gpu.stats.cpu().numpy(), cpu.stats)
+
+
+@pytest.mark.parametrize("size,n,p", [("small", 4097, 0.0), ("medium", 1000, 0.25), ("large", 515, 0.0)])
+def test_multi_step_greedy_rollout_kernel(size, n, p):
+    """wh_greedy_rollout: T solver+step iterations in one launch (state in registers, no per-step
+    observations) == T wh_greedy_step launches: state, statistics, dones, reward sums; across two
+    episode boundaries (in-kernel auto-reset), with and without the eps-random branch."""
+    from rllib_warehouse_b200 import VARIANTS, BatchedWarehouse
+    one = BatchedWarehouse(VARIANTS[size], n, seed=31, auto_reset=True)
+    many = BatchedWarehouse(VARIANTS[size], n, seed=31, auto_reset=True)
+    one.reset(); many.reset()
+    total = torch.zeros_like(many.rewards)
+    done_steps = 0
+    for chunk in (1, 7, 192, 150, 100):                 # 450 steps: crosses t = 200 and t = 400
+        rs = one.greedy_rollout(chunk, random_action_prob=p, solver_seed=5).clone()
+        acc = torch.zeros_like(rs)
+        for _ in range(chunk):
+            many.greedy_step(random_action_prob=p, solver_seed=5, want_actions=False)
+            acc += many.rewards
+        done_steps += chunk
+        assert torch.equal(rs, acc), f"reward sums after {done_steps} steps"
+        assert torch.equal(one.dones, many.dones)
+        a, b = one.get_state(), many.get_state()
+        for k in a:
+            assert np.array_equal(a[k], b[k]), f"state {k} after {done_steps} steps"
+        for k in gu.OBS_KEYS:                           # rebuilt from the final state
+            if int(many.dones.max()) == 0:              # (a just-reset env shows its reset flavour in `many`)
+                assert torch.equal(one.obs[k], many.obs[k]), f"obs {k} after {done_steps} steps"
+        total += rs
+    assert torch.equal(one.stats, many.stats) and int(one.stats[0]) == 2 * n
+    if p == 0.0 and n <= 4097:
+        cpu = wo.OracleEnv(wo.variant_config(size), n, seed=31)
+        cpu.reset()
+        for t in range(450):
+            cpu.greedy(); cpu.step(cpu.actions)
+            done = cpu.dones.astype(bool)
+            if done.any():
+                cpu.reset(env_mask=done.astype(np.uint8))
+        same_state(one, cpu, "rollout kernel vs oracle")
+        assert np.array_equal(one.stats.cpu().numpy(), cpu.stats)
