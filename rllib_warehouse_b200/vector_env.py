@@ -60,20 +60,20 @@ class WarehouseVectorEnv(BaseEnv):
     def _host_obs(self, flavour, envs=None):
         """Per-env, per-agent observation dicts (or flat vectors) on the host."""
         A = self.env.state["num_agents"].cpu().numpy()
+        host = self.env.outputs_to_host()           # every key + rewards + dones: ONE device->host copy
         if self.flat_obs:
             flat = self.env.build_obs_flat(flavour).cpu().numpy()
             get = lambda e, i: flat[e, i]
-        else:
-            host = {k: self.env.obs[k].cpu().numpy() for k in OBS_KEYS}
-            get = lambda e, i: {k: host[k][e, i] for k in OBS_KEYS}
+        else:                                       # fresh arrays: the pinned buffer is reused next step
+            get = lambda e, i: {k: host[k][e, i].copy() for k in OBS_KEYS}
         envs = range(self.num_envs) if envs is None else envs
-        return {e: {str(i): get(e, i) for i in range(int(A[e]))} for e in envs}, A
+        return {e: {str(i): get(e, i) for i in range(int(A[e]))} for e in envs}, host
 
     def poll(self):
         if not self._initialized:
             self.env.reset()
             self._initialized = True
-            obs, A = self._host_obs(nv.OBS_RESET)
+            obs, _ = self._host_obs(nv.OBS_RESET)
             rewards = {e: {a: None for a in obs[e]} for e in obs}
             dones = {e: {**{a: False for a in obs[e]}, "__all__": False} for e in obs}
             infos = {e: {a: {} for a in obs[e]} for e in obs}
@@ -95,9 +95,9 @@ class WarehouseVectorEnv(BaseEnv):
                 self._order[e, t] = i
                 ascending &= t == 0 or self._order[e, t - 1] < i
         self.env.step(self._actions, order=None if ascending else self._order, with_obs=not self.flat_obs)
-        obs, A = self._host_obs(nv.OBS_STEP, envs=list(action_dict.keys()))
-        rew = self.env.rewards.cpu().numpy()
-        done = self.env.dones.cpu().numpy().astype(bool)
+        obs, host = self._host_obs(nv.OBS_STEP, envs=list(action_dict.keys()))
+        rew = host["rewards"].copy()
+        done = host["dones"].astype(bool)
         rewards = {e: {a: rew[e, int(a)] for a in obs[e]} for e in obs}
         dones = {e: {**{a: bool(done[e]) for a in obs[e]}, "__all__": bool(done[e])} for e in obs}
         infos = {e: {a: {} for a in obs[e]} for e in obs}
