@@ -19,6 +19,9 @@ OBS_KEYS = nv.OBS_KEYS
 def _dev_tensor(x, dtype, device, shape=None):
     if x is None:
         return None
+    if (isinstance(x, torch.Tensor) and x.dtype == dtype and x.device == device and x.is_contiguous()
+            and (shape is None or tuple(x.shape) == tuple(shape))):
+        return x                              # the per-step fast path: already what the kernel needs
     if not isinstance(x, torch.Tensor):
         x = torch.from_numpy(np.ascontiguousarray(x))
     x = x.to(device=device, dtype=dtype).contiguous()
@@ -69,6 +72,27 @@ class Arena:
         return self.views
 
 
+class _OnDevice:
+    """`with torch.cuda.device(d)` costs several microseconds per launch; the current device already
+    is `d` in the one-process-per-GPU setting, so only switch when it is not."""
+    __slots__ = ("index", "ctx")
+
+    def __init__(self, device):
+        self.index, self.ctx = device.index if device.index is not None else torch.cuda.current_device(), None
+
+    def __enter__(self):
+        if torch.cuda.current_device() != self.index:
+            self.ctx = torch.cuda.device(self.index)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            ctx, self.ctx = self.ctx, None
+            ctx.__exit__(*exc)
+        return False
+
+
 class BatchedWarehouse:
     """Structure-of-arrays state + observation tensors for `num_envs` environments on one GPU.
 
@@ -87,8 +111,11 @@ class BatchedWarehouse:
         self.N = int(num_envs)
         self.R, self.P, self.D = config.num_requests, config.num_pickup_points, config.num_delivery_points
         self.device = torch.device(device)
+        if self.device.index is None:          # "cuda" -> "cuda:<current>", so that device comparisons hold
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.seed, self.env_id0 = int(seed) & (2**64 - 1), int(env_id0)
         self.auto_reset = bool(auto_reset)
+        self._on_device = _OnDevice(self.device)
         self._cfg = nv.make_config(config)
         N, R, P, dev = self.N, self.R, self.P, self.device
         A0 = config.max_num_agents if num_agents is None else int(num_agents)
@@ -144,7 +171,7 @@ class BatchedWarehouse:
         num_agents = _dev_tensor(num_agents, i8, dev, (N,))
         env_mask = _dev_tensor(env_mask, torch.uint8, dev, (N,))
         keep = (agent_pos, init_pickups, init_targets, num_agents, env_mask)  # alive until launch returns
-        with torch.cuda.device(dev):
+        with self._on_device:
             rc = self.lib.wh_reset(C.byref(self._cfg), C.byref(self._st), N, self.env_id0, self.seed,
                                    _ptr(agent_pos), _ptr(init_pickups), _ptr(init_targets),
                                    _ptr(num_agents), _ptr(env_mask),
@@ -162,7 +189,7 @@ class BatchedWarehouse:
         spawn_pickups = _dev_tensor(spawn_pickups, torch.int8, dev, (N, R))
         spawn_targets = _dev_tensor(spawn_targets, torch.int8, dev, (N, R))
         flags = nv.FLAG_AUTO_RESET if (self.auto_reset and spawn_pickups is None) else 0
-        with torch.cuda.device(dev):
+        with self._on_device:
             rc = self.lib.wh_step(C.byref(self._cfg), C.byref(self._st), N, self.env_id0, self.seed,
                                   _ptr(actions), _ptr(order), _ptr(spawn_pickups), _ptr(spawn_targets),
                                   self.rewards.data_ptr(), self.dones.data_ptr(), self.stats.data_ptr(),
@@ -182,7 +209,7 @@ class BatchedWarehouse:
                 self._flat = torch.empty((N, R, 9 * R + 1), dtype=torch.float32, device=dev)
             out = self._flat
         flags = nv.FLAG_AUTO_RESET if self.auto_reset else 0
-        with torch.cuda.device(dev):
+        with self._on_device:
             rc = self.lib.wh_step_flat(C.byref(self._cfg), C.byref(self._st), N, self.env_id0, self.seed,
                                        _ptr(actions), _ptr(order), self.rewards.data_ptr(),
                                        self.dones.data_ptr(), self.stats.data_ptr(), out.data_ptr(),
@@ -196,7 +223,7 @@ class BatchedWarehouse:
         (solvers.py:27-58) evaluated from the resident state, then step + observation build."""
         thr = int(float(random_action_prob) * 4294967296.0)
         flags = nv.FLAG_AUTO_RESET if self.auto_reset else 0
-        with torch.cuda.device(self.device):
+        with self._on_device:
             rc = self.lib.wh_greedy_step(C.byref(self._cfg), C.byref(self._st), self.N, self.env_id0,
                                          self.seed, int(solver_seed), thr,
                                          self.actions.data_ptr() if want_actions else None,
@@ -215,7 +242,7 @@ class BatchedWarehouse:
         resident observations from the final state afterwards (one more launch)."""
         thr = int(float(random_action_prob) * 4294967296.0)
         flags = nv.FLAG_AUTO_RESET if self.auto_reset else 0
-        with torch.cuda.device(self.device):
+        with self._on_device:
             rc = self.lib.wh_greedy_rollout(C.byref(self._cfg), C.byref(self._st), self.N, self.env_id0,
                                             self.seed, int(solver_seed), thr, int(steps),
                                             self.rewards.data_ptr(), self.dones.data_ptr(),
@@ -227,7 +254,7 @@ class BatchedWarehouse:
         return self.rewards
 
     def build_obs(self, flavour=nv.OBS_STEP):
-        with torch.cuda.device(self.device):
+        with self._on_device:
             rc = self.lib.wh_build_obs(C.byref(self._cfg), C.byref(self._st), self.N, int(flavour),
                                        C.byref(self._ob), self._stream())
         nv.check(rc, "wh_build_obs")
@@ -243,7 +270,7 @@ class BatchedWarehouse:
             if getattr(self, "_flat", None) is None:
                 self._flat = torch.empty((N, R, 9 * R + 1), dtype=torch.float32, device=self.device)
             out = self._flat
-        with torch.cuda.device(self.device):
+        with self._on_device:
             rc = self.lib.wh_build_obs_flat(C.byref(self._cfg), C.byref(self._st), N,
                                             nv.OBS_STEP if flavour is None else int(flavour),
                                             out.data_ptr(), self._stream())
@@ -272,7 +299,7 @@ class BatchedWarehouse:
         random_actions = _dev_tensor(random_actions, torch.int32, dev, (N, R))
         out = self.actions if out is None else out
         thr = int(float(random_action_prob) * 4294967296.0)
-        with torch.cuda.device(dev):
+        with self._on_device:
             rc = self.lib.wh_greedy(C.byref(self._cfg), C.byref(ob), self.state["num_agents"].data_ptr(),
                                     self.state["episode"].data_ptr(), self.state["time"].data_ptr(),
                                     N, self.env_id0, int(solver_seed), thr, _ptr(is_random),
