@@ -18,6 +18,8 @@ path) and compares the CRCs. Batches (committed under tests/golden/batch_*.npz):
   small_random   4096 envs x 200 steps, A = 4, random actions          (configs[1])
   medium_greedy  1024 envs x 200 steps, A = 9, reference greedy solver (configs[2] replay subset)
   large_random    512 envs x 200 steps, A = 16, random actions         (configs[3] replay subset)
+  small_train_greedy / large_train_random   2048 / 256 envs of the *Train variants: per-env random agent
+                 count (rows >= A of every [N,R,...] array are padding and hold -1 / 0 in the digest)
 
     python oracle/make_golden_batch.py      # needs /root/reference; ~2 min on 8 cores
 """
@@ -39,6 +41,9 @@ BATCHES = {
     "small_random": dict(size="small", n=4096, policy="random"),
     "medium_greedy": dict(size="medium", n=1024, policy="greedy"),
     "large_random": dict(size="large", n=512, policy="random"),
+    # *Train variants (variants.py:65-98): the agent count is redrawn per env, rows >= A are padding
+    "small_train_greedy": dict(size="small", n=2048, policy="greedy", train=True),
+    "large_train_random": dict(size="large", n=256, policy="random", train=True),
 }
 STATE_KEYS = ("agent_pos", "agent_tgt", "pickup_tgt", "pickup_timer", "time", "num_agents")
 OUT_KEYS = STATE_KEYS + tuple("obs_" + k for k in mg.OBS_KEYS) + ("actions", "rewards", "dones")
@@ -53,18 +58,20 @@ def canon_dtype(k):
 
 
 def _one_env(args):
-    size, e, policy, actions = args
-    cls, _ = mg.VARIANTS[size]
-    A = cls.max_num_agents
+    size, e, policy, actions, train = args
+    cls, train_cls = mg.VARIANTS[size]
     np.random.seed(BASE_SEED + e)
     with mg.ChoiceRecorder() as rec:
-        env = cls(A)
+        env = train_cls() if train else cls(cls.max_num_agents)
         rec.take()
         obs = env.reset()
+        A = env.num_agents                      # *Train: redrawn by reset (variants.py:69-74)
         R = env.num_requests
         init_p, init_t = rec.take()
         solver = mg.WarehouseRandomGreedySolver(A, R, 0.0, env.action_space)
-        out = dict(reset_agent_pos=env._agent_positions.astype(np.int8).copy(),
+        pos0 = np.full((R, 2), -1, np.int8)
+        pos0[:A] = env._agent_positions
+        out = dict(reset_agent_pos=pos0, reset_num_agents=np.int8(A),
                    reset_init_pickups=init_p.astype(np.int8), reset_init_targets=init_t.astype(np.int8))
         reset_rec = dict(mg.snap_state(env, R))
         reset_rec.update(mg.snap_obs(obs, A, R))
@@ -72,9 +79,9 @@ def _one_env(args):
         for t in range(T):
             if policy == "greedy":
                 ad = solver.compute_action(obs)
-                act = np.array([int(ad[str(i)]) for i in range(A)], np.int32)
+                act = mg.pad([int(ad[str(i)]) for i in range(A)], R)
             else:
-                act = actions[t]
+                act = mg.pad(actions[t][:A], R)
                 ad = {str(i): int(act[i]) for i in range(A)}
             obs, rew, dones, _ = env.step(ad)
             sp, st = rec.take()
@@ -82,7 +89,7 @@ def _one_env(args):
                      actions=act.astype(np.int8))
             r.update(mg.snap_state(env, R))
             r.update(mg.snap_obs(obs, A, R))
-            r["rewards"] = np.array([rew[str(i)] for i in range(A)], np.float32)
+            r["rewards"] = np.array([rew[str(i)] for i in range(A)] + [0.0] * (R - A), np.float32)
             r["dones"] = np.uint8(dones["__all__"])
             steps.append(r)
     out["reset"] = mg.shrink(reset_rec)
@@ -90,16 +97,17 @@ def _one_env(args):
     return out
 
 
-def make_batch(name, size, n, policy, pool):
+def make_batch(name, size, n, policy, pool, train=False):
     cls, _ = mg.VARIANTS[size]
     A = cls.max_num_agents
     actions = np.random.Generator(np.random.PCG64(SEED_A)).integers(0, 9, size=(T, n, A)).astype(np.int32)
-    res = pool.map(_one_env, [(size, e, policy, actions[:, e] if policy == "random" else None)
+    res = pool.map(_one_env, [(size, e, policy, actions[:, e] if policy == "random" else None, train)
                               for e in range(n)], chunksize=16)
     fx = dict(mg.env_dims(cls(A)))
     fx.update(n=np.int32(n), T=np.int32(T), A=np.int32(A), base_seed=np.int64(BASE_SEED),
-              seed_actions=np.int64(SEED_A), policy=np.array(policy), out_keys=np.array(OUT_KEYS))
-    for k in ("reset_agent_pos", "reset_init_pickups", "reset_init_targets"):
+              seed_actions=np.int64(SEED_A), policy=np.array(policy), out_keys=np.array(OUT_KEYS),
+              train=np.int8(train))
+    for k in ("reset_agent_pos", "reset_init_pickups", "reset_init_targets", "reset_num_agents"):
         fx[k] = np.stack([r[k] for r in res])
     for k in ("spawn_pickups", "spawn_targets"):
         fx[k] = np.stack([r["steps"][k] for r in res], axis=1)               # [T, n, R]

@@ -147,13 +147,20 @@ def check_batch_digests(make_env, d, greedy_fn=None, steps=None):
     n, A, R = int(d["n"]), int(d["A"]), int(d["R"])
     T = int(d["T"]) if steps is None else steps
     policy = str(d["policy"])
-    env = make_env(cfg_kwargs(d), n, A)
+    # per-env agent counts (the *Train batches; all equal to A otherwise); rows >= num_agents are
+    # padding the reference never produces: -1 in the digest
+    num_agents = d["reset_num_agents"].astype(np.int32) if "reset_num_agents" in d else np.full(n, A, np.int32)
+    pad_rows = np.arange(R)[None, :] >= num_agents[:, None]
+    env = make_env(cfg_kwargs(d), n, None if pad_rows.any() else A)
     obs = env.reset(agent_pos=d["reset_agent_pos"], init_pickups=d["reset_init_pickups"],
-                    init_targets=d["reset_init_targets"], num_agents=np.full(n, A, np.int32))
+                    init_targets=d["reset_init_targets"], num_agents=num_agents)
 
     def outputs(obs):
         out = dict(get_state(env))
-        out.update({"obs_" + k: obs[k] for k in OBS_KEYS})
+        for k in OBS_KEYS:
+            v = _np(obs[k]).astype(np.int32).copy()
+            v[pad_rows] = -1
+            out["obs_" + k] = v
         return out
 
     got = outputs(obs)
@@ -163,14 +170,15 @@ def check_batch_digests(make_env, d, greedy_fn=None, steps=None):
     keys = [str(k) for k in d["out_keys"]]
     ret = np.zeros(n, np.float64)
     for t in range(T):
-        acts = _np(greedy_fn(env))[:, :A].astype(np.int32) if policy == "greedy" else acts_all[t]
+        acts = (_np(greedy_fn(env))[:, :R] if policy == "greedy" else acts_all[t]).astype(np.int32).copy()
+        acts[pad_rows] = -1
         obs, rew, dones = env.step(acts, spawn_pickups=d["spawn_pickups"][t], spawn_targets=d["spawn_targets"][t])
         got = outputs(obs)
-        got.update(actions=acts, rewards=_np(rew)[:, :A], dones=_np(dones))
+        got.update(actions=acts, rewards=_np(rew)[:, :R], dones=_np(dones))
         for j, k in enumerate(keys):
             dt = np.float32 if k == "rewards" else (np.uint8 if k == "dones" else np.int32)
             assert _crc(got[k], dt) == int(d["step_crc"][t, j]), f"step {t}: '{k}' differs from the reference"
-        ret += _np(rew)[:, :A].sum(axis=1)
+        ret += _np(rew)[:, :R].sum(axis=1)
     if T == int(d["T"]):
         assert_state(env, {k: d["final_" + k] for k in STATE_KEYS}, "final state")
         assert np.array_equal(ret.astype(np.float32), d["return_per_env"])

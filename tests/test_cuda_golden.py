@@ -43,7 +43,7 @@ def test_solver(size):
     assert gu.check_solver(greedy_fn, gu.load(f"solver_{size}.npz")) == 120
 
 
-@pytest.mark.parametrize("name", ["small_random", "medium_greedy", "large_random"])
+@pytest.mark.parametrize("name", ["small_random", "medium_greedy", "large_random", "small_train_greedy", "large_train_random"])
 def test_full_size_reference_digests(name):
     """BASELINE configs[1] exactly as SURVEY §8d config 2 states it — 4 096 Small envs, 200 steps,
     env e = the unmodified reference seeded with BASE+e, PCG64 action tensor — plus the Medium

@@ -59,7 +59,7 @@ def test_solver(size):
     assert np.array_equal(pure[:, : d["actions"].shape[1]][keep], d["actions"][keep])
 
 
-@pytest.mark.parametrize("name", ["small_random", "medium_greedy", "large_random"])
+@pytest.mark.parametrize("name", ["small_random", "medium_greedy", "large_random", "small_train_greedy", "large_train_random"])
 def test_full_size_reference_digests(name):
     """BASELINE configs[1] at full size (4 096 Small envs x 200 steps) and the configs[2]/[3] replay
     subsets: the C oracle reproduces the reference's per-step CRCs of every output array."""
