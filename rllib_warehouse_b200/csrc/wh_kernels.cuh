@@ -963,15 +963,18 @@ __device__ __forceinline__ int greedy_from_state(const KParams &P, const Group<G
     const int nact = __popcll(active);
     uint32_t cell = geo.null16();
     if (g.gl < nact && g.gl < R) cell = pickup_cell16(P, geo, nth_set64<Group<GC>::PBITS>(active, g.gl));
-    int best = 1 << 30;
-    uint32_t bcell = 0;
+    // L1 argmin with first-minimum tie-break (solvers.py:53-58) as a running minimum of the key
+    // distance << 21 | request index << 16 | cell. The distance of two packed cells (x | y << 8, upper
+    // bytes zero) is ONE instruction: the byte-wise sum of absolute differences (VABSDIFF4.U8.ACC).
+    uint32_t best = 0xFFFFFFFFu;
     const int RR = RC ? RC : R;
 #pragma unroll
-    for (int r = 0; r < RR; ++r) {                                             // solvers.py:53-58
+    for (int r = 0; r < RR; ++r) {
         const uint32_t c = g.shfl(cell, r);
-        const int d = abs(px - (int)(c & 0xFF)) + abs(py - (int)(c >> 8));
-        if (d < best) { best = d; bcell = c; }
+        const uint32_t d = __vsadu4(s.pos16 & 0xFFFFu, c);
+        best = min(best, (d << 21) + (((uint32_t)r << 16) | c));
     }
+    const uint32_t bcell = best & 0xFFFFu;
     uint32_t target;
     const bool free_agent = s.time > 0 && s.atgt == -1;                        // availability 1
     if (free_agent) target = bcell;
