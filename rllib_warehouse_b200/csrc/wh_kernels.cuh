@@ -304,9 +304,16 @@ struct EnvRegs {
     uint32_t pos16;  // my agent's cell (x | y<<8), 0xFFFF for rows >= A
     int atgt;        // my agent's delivery target or -1
     uint32_t pt4;    // delivery targets of my 4 pickup points (0xFF = inactive)
-    int tm[4];       // their timers
+    uint2 tmr;       // their timers as loaded: four int16, t0 | t1 << 16, t2 | t3 << 16 (0xFFFF = -1 = none)
     int time, A, ep;
 };
+
+// timer j of a lane := v (16 bits); j is a runtime index into the two packed registers
+__device__ __forceinline__ void set_timer(EnvRegs &s, int j, uint32_t v) {
+    const uint32_t sh = (uint32_t)(j & 1) * 16u, m = 0xFFFFu << sh, val = (v & 0xFFFFu) << sh;
+    if (j < 2) s.tmr.x = (s.tmr.x & ~m) | val;
+    else s.tmr.y = (s.tmr.y & ~m) | val;
+}
 
 // PP = number of pickup points: a compile-time 4*G in the variant kernels, P.P otherwise
 template <int GC>
@@ -321,12 +328,10 @@ __device__ __forceinline__ void load_env(const KParams &P, const Group<GC> &g, e
         s.atgt = P.agent_tgt[e * R + g.gl];
     }
     s.pt4 = 0xFFFFFFFFu;
-    s.tm[0] = s.tm[1] = s.tm[2] = s.tm[3] = -1;
+    s.tmr = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
     if (4 * g.gl < PP) {
         s.pt4 = reinterpret_cast<const uint32_t *>(P.pickup_tgt + e * PP)[g.gl];
-        const uint2 t = reinterpret_cast<const uint2 *>(P.pickup_timer + e * PP)[g.gl];
-        s.tm[0] = (int16_t)(t.x & 0xFFFF); s.tm[1] = (int16_t)(t.x >> 16);
-        s.tm[2] = (int16_t)(t.y & 0xFFFF); s.tm[3] = (int16_t)(t.y >> 16);
+        s.tmr = reinterpret_cast<const uint2 *>(P.pickup_timer + e * PP)[g.gl];
     }
 }
 
@@ -339,10 +344,7 @@ __device__ __forceinline__ void store_env(const KParams &P, const Group<GC> &g, 
     }
     if (4 * g.gl < PP) {
         reinterpret_cast<uint32_t *>(P.pickup_tgt + e * PP)[g.gl] = s.pt4;
-        uint2 t;
-        t.x = (uint32_t)(s.tm[0] & 0xFFFF) | ((uint32_t)(s.tm[1] & 0xFFFF) << 16);
-        t.y = (uint32_t)(s.tm[2] & 0xFFFF) | ((uint32_t)(s.tm[3] & 0xFFFF) << 16);
-        reinterpret_cast<uint2 *>(P.pickup_timer + e * PP)[g.gl] = t;
+        reinterpret_cast<uint2 *>(P.pickup_timer + e * PP)[g.gl] = s.tmr;
     }
     if (g.gl == 0) {
         P.time[e] = s.time;
@@ -440,14 +442,28 @@ __device__ __forceinline__ StepOut do_world(const KParams &P, const Group<GC> &g
     StepOut o;
     const Geo<GC> geo(P);
     // ---- core.py:303-306 expiry (before pickup detection) ----
+    // The four timers stay packed as loaded. Point j is active iff bit 7 of byte j of pt4 is clear;
+    // -1 is added to the active halves with the packed 16-bit add (VIADD.16x2: no borrow between the
+    // halves), and a half that reached 0 — found with the packed unsigned minimum — has expired.
     int nexp = 0;
+    {
+        const uint32_t inv = ~s.pt4;
+        const uint32_t d0 = ((inv >> 7) & 1u) * 0xFFFFu + ((inv >> 15) & 1u) * 0xFFFF0000u;
+        const uint32_t d1 = ((inv >> 23) & 1u) * 0xFFFFu + ((inv >> 31) & 1u) * 0xFFFF0000u;
+        s.tmr.x = __vadd2(s.tmr.x, d0);
+        s.tmr.y = __vadd2(s.tmr.y, d1);
+        const bool any0 = (__vminu2(s.tmr.x, 0x00010001u) & __vminu2(s.tmr.y, 0x00010001u)) != 0x00010001u;
+        if (__any_sync(FULL, any0)) {               // rare: a request expires at most once per episode
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const bool act = ((s.pt4 >> (8 * j + 7)) & 1u) == 0u;
-        s.tm[j] -= act ? 1 : 0;
-        if (s.tm[j] == 0) { s.pt4 |= 0xFFu << (8 * j); s.tm[j] = -1; ++nexp; }
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t t = ((j < 2 ? s.tmr.x : s.tmr.y) >> (16 * (j & 1))) & 0xFFFFu;
+                if (t == 0u) { s.pt4 |= 0xFFu << (8 * j); set_timer(s, j, 0xFFFFu); ++nexp; }
+            }
+            o.nexp = g.add(nexp);
+        } else {
+            o.nexp = 0;
+        }
     }
-    o.nexp = __any_sync(FULL, nexp != 0) ? g.add(nexp) : 0;
     // ---- core.py:309-335 pickups: agent on a pickup cell, free, request waiting there ----
     const int x = s.pos16 & 0xFF, y = s.pos16 >> 8;
     const int cand = (g.gl < s.A) ? pickup_index(P, geo, x, y) : -1;
@@ -461,7 +477,7 @@ __device__ __forceinline__ StepOut do_world(const KParams &P, const Group<GC> &g
         const uint32_t nib = (g.gl < 16) ? (uint32_t)((served >> (4 * g.gl)) & 0xFull) : 0u;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-            if ((nib >> j) & 1u) { s.pt4 |= 0xFFu << (8 * j); s.tm[j] = -1; }  // core.py:330-331
+            if ((nib >> j) & 1u) { s.pt4 |= 0xFFu << (8 * j); set_timer(s, j, 0xFFFFu); }  // core.py:330-331
         if (picks) { s.atgt = tg; reward = 1.0f; }                             // core.py:327-329,335
         o.npick = __popc(g.ballot(picks));
     }
@@ -501,8 +517,7 @@ __device__ __forceinline__ StepOut do_world(const KParams &P, const Group<GC> &g
                 if ((p >> 2) == g.gl) {                                       // core.py:344,351
                     const int j = p & 3;
                     s.pt4 = (s.pt4 & ~(0xFFu << (8 * j))) | (((uint32_t)d & 0xFFu) << (8 * j));
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) if (jj == j) s.tm[jj] = P.wait;
+                    set_timer(s, j, (uint32_t)P.wait);
                 }
             }
         }
@@ -908,7 +923,7 @@ __device__ __forceinline__ unsigned long long do_reset(const KParams &P, const G
         }
     }
     n.pt4 = 0xFFFFFFFFu;                                                       // core.py:210-211
-    n.tm[0] = n.tm[1] = n.tm[2] = n.tm[3] = -1;
+    n.tmr = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
     // core.py:215-221 R distinct pickup points x R distinct delivery points, paired in draw order
     int sp = -1, st_ = -1;
     if (replay) {
@@ -936,8 +951,7 @@ __device__ __forceinline__ unsigned long long do_reset(const KParams &P, const G
             if ((p >> 2) == g.gl) {
                 const int j = p & 3;
                 n.pt4 = (n.pt4 & ~(0xFFu << (8 * j))) | (((uint32_t)d & 0xFFu) << (8 * j));
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) if (jj == j) n.tm[jj] = P.wait;
+                set_timer(n, j, (uint32_t)P.wait);
             }
         }
     }
