@@ -384,14 +384,14 @@ __device__ __forceinline__ void do_moves(const KParams &P, const Group<GC> &g, i
         if ((unsigned)x >= (unsigned)geo.dim) x = px;  // per-axis clamp => wall sliding (core.py:284-287)
         if ((unsigned)y >= (unsigned)geo.dim) y = py;
         const uint32_t to = (uint32_t)x | ((uint32_t)y << 8);
-        m = pos16 | (to << 16);
-        rev = to | (pos16 << 16);                                              // core.py:294
-        ca = cb = rev;
-        if (x != px && y != py) {                                              // core.py:295-297
-            const uint32_t c1 = (uint32_t)x | ((uint32_t)py << 8), c2 = (uint32_t)px | ((uint32_t)y << 8);
-            ca = c1 | (c2 << 16);
-            cb = c2 | (c1 << 16);
-        }
+        m = pos16 | (to << 16);                                // bytes [px, py, x, y]
+        // the forbidden moves are byte permutations of m: the reverse move [x, y, px, py] (core.py:294)
+        // and, for a diagonal, the two crossing moves (x,py)->(px,y) = [x, py, px, y] and
+        // (px,y)->(x,py) = [px, y, x, py] (core.py:295-297); otherwise all three are the reverse move
+        const bool diag = x != px && y != py;
+        rev = __byte_perm(m, 0u, 0x1032u);
+        ca = __byte_perm(m, 0u, diag ? 0x3012u : 0x1032u);
+        cb = __byte_perm(m, 0u, diag ? 0x1230u : 0x1032u);
     }
     uint32_t mark = (g.gl < A) ? pos16 : NO_CELL;   // core.py:276: every agent marks its cell
     uint32_t moved = 0u;  // arms rev / ca / cb (an ABSENT move is rejected below whatever `hit` says)
