@@ -13,7 +13,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_multiagent_env_contract():
     import warehouse
-    from rllib_warehouse_b200 import spaces
     assert set(warehouse.__all__) == {"Warehouse", "WarehouseSmall", "WarehouseMedium", "WarehouseLarge",
                                       "WarehouseSmallTrain", "WarehouseMediumTrain", "WarehouseLargeTrain"}
     np.random.seed(3)
