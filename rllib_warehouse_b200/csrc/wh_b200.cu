@@ -98,7 +98,9 @@ __device__ __forceinline__ void account_episode(const KParams &P, bool owner, en
 
 // Warehouse.step (+ optional in-kernel greedy solver, + optional observation build, + optional
 // auto-reset) — core.py:262-442, solvers.py:27-58
-template <int GC, int RC, bool GREEDY, bool FLAT>
+// PLAIN: the caller passes int32 actions / float32 rewards, no dict order and no replayed draws (the
+// throughput path); the instantiation then carries none of the code or tests for those options.
+template <int GC, int RC, bool GREEDY, bool FLAT, bool PLAIN = false>
 __global__ void __launch_bounds__(BLOCK, (RC == 16 ? WH_MIN_BLOCKS_LARGE : RC == 9 ? WH_MIN_BLOCKS_MEDIUM : RC == 4 ? WH_MIN_BLOCKS_SMALL : WH_MIN_BLOCKS)) k_step(const __grid_constant__ KParams P) {
     __shared__ __align__(16) unsigned char smem[StageMem<GC, RC, FLAT>::BYTES];
     // Programmatic dependent launch (launch_step): the next step's blocks may be scheduled while
@@ -119,20 +121,20 @@ __global__ void __launch_bounds__(BLOCK, (RC == 16 ? WH_MIN_BLOCKS_LARGE : RC ==
         act = greedy_from_state<GC, RC>(P, g, R, env_id, s);
         if (P.actions_out && t.live && g.gl < R) P.actions_out[e * R + g.gl] = act;
     } else if (g.gl < R) {
-        act = (P.flags & WH_FLAG_COMPACT_IO) ? (int)reinterpret_cast<const int8_t *>(P.actions)[e * R + g.gl]
-                                             : P.actions[e * R + g.gl];
-        if (P.order) ord = P.order[e * R + g.gl];
+        act = (!PLAIN && (P.flags & WH_FLAG_COMPACT_IO)) ? (int)reinterpret_cast<const int8_t *>(P.actions)[e * R + g.gl]
+                                                          : P.actions[e * R + g.gl];
+        if (!PLAIN && P.order) ord = P.order[e * R + g.gl];
     }
     s.time += 1;                                                               // core.py:267
-    do_moves<GC, RC>(P, g, R, s.A, act, ord, !GREEDY && P.order != nullptr, s.pos16);
-    const StepOut so = do_world(P, g, e, R, env_id, s, !GREEDY && P.spawn_p != nullptr);
+    do_moves<GC, RC>(P, g, R, s.A, act, ord, !PLAIN && !GREEDY && P.order != nullptr, s.pos16);
+    const StepOut so = do_world(P, g, e, R, env_id, s, !PLAIN && !GREEDY && P.spawn_p != nullptr);
     unsigned long long active = so.active;
     uint32_t tpos16 = so.tpos16;
 
     const bool done = s.time >= P.episode;                                     // core.py:438
     if (t.live) {
         if (g.gl < R) {                                                         // core.py:435
-            if (P.flags & WH_FLAG_COMPACT_IO) reinterpret_cast<uint8_t *>(P.rewards)[e * R + g.gl] = (uint8_t)so.reward;
+            if (!PLAIN && (P.flags & WH_FLAG_COMPACT_IO)) reinterpret_cast<uint8_t *>(P.rewards)[e * R + g.gl] = (uint8_t)so.reward;
             else P.rewards[e * R + g.gl] = so.reward;
         }
         if (g.gl == 0) P.dones[e] = done ? 1 : 0;
@@ -408,12 +410,21 @@ static void launch_kind(Kind kind, const KParams &K, cudaStream_t s) {
         if (dev >= 0 && dev < 64 && !done[dev]) {
             cudaFuncSetAttribute(k_step<GC, RC, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
             cudaFuncSetAttribute(k_step<GC, RC, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+            cudaFuncSetAttribute(k_step<GC, RC, false, false, RC != 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+            cudaFuncSetAttribute(k_step<GC, RC, true, false, RC != 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
             done[dev] = true;
         }
     }
+    const bool plain = RC != 0 && !(K.flags & WH_FLAG_COMPACT_IO) && !K.order && !K.spawn_p;
     switch (kind) {
-    case K_STEP: launch_step(k_step<GC, RC, false, false>, grid, dyn, s, K); break;
-    case K_GSTEP: launch_step(k_step<GC, RC, true, false>, grid, dyn, s, K); break;
+    case K_STEP:
+        if (plain) launch_step(k_step<GC, RC, false, false, RC != 0>, grid, dyn, s, K);
+        else launch_step(k_step<GC, RC, false, false>, grid, dyn, s, K);
+        break;
+    case K_GSTEP:
+        if (plain) launch_step(k_step<GC, RC, true, false, RC != 0>, grid, dyn, s, K);
+        else launch_step(k_step<GC, RC, true, false>, grid, dyn, s, K);
+        break;
     case K_STEP_FLAT: launch_step(k_step<GC, RC, false, true>, grid, 0, s, K); break;
     case K_RESET: k_reset<GC, RC><<<grid, BLOCK, 0, s>>>(K); break;
     case K_OBS: k_obs<GC, RC><<<grid, BLOCK, 0, s>>>(K); break;
