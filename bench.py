@@ -2,7 +2,8 @@
 """bench.py — agent-steps/s of the batched warehouse env.step on N B200s, beside the CPU reference.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
-    python bench.py --impl reference [--steps K] [--warmup W]      # CPU arm (oracle port, all host threads)
+    python bench.py --impl reference [--steps K] [--warmup W]      # CPU arm: the unmodified reference (oracle/_ref)
+                                                                   # on every host core, C port beside it
     torchrun --nproc-per-node N ... bench.py --gpus N ...          # one rank per GPU
 
 Workload (BASELINE.json configs[3]): WarehouseLarge, 16 agents, 262 144 envs per GPU, contiguous
@@ -10,11 +11,18 @@ global env-id shards, no data-path collective (weak scaling: per-GPU work is fix
 `--scaling strong` splits a fixed total of 262 144 envs over the GPUs instead). A "step" is
 one `env.step` of every env: the fused move/collision/expiry/pickup/respawn/delivery kernel with
 the observation build, on int32 actions already resident in HBM (uniform-random; a pool of 200
-action tensors = one full episode of distinct actions, cycled). Observations (2.2 GB per step in total) are larger than L2, so no flush
-is needed between iterations. `e2e` is the same step through the host-buffer C ABI
-(`wh_env_step_host`): actions come from pinned host memory every step and rewards + dones go
-back to pinned host memory every step; observations stay in HBM for an on-device policy.
-Prints ONE JSON line (rank 0).
+action tensors = one full episode of distinct actions, cycled). Observations (2.2 GB per step in
+total) are larger than L2, so no flush is needed between iterations.
+
+Timed region: barrier + synchronize, CUDA event, exactly K steps (one k_step launch each), CUDA event,
+max over ranks. The end-of-rollout NCCL reduction of the episode statistics (`wh_stats_allreduce`) is
+issued once during warm-up and once after the K steps inside its own event pair (`collective_ms`).
+
+`e2e` is the same step through the host-buffer C ABI (`wh_env_step_host`) with the reference's wire
+dtypes: int32 actions come from pinned host memory every step, float32 rewards + dones go back to
+pinned host memory every step, observations stay in HBM for an on-device policy. `e2e_alt` is the same
+with the int8/uint8 wire format, `e2e_host_obs` additionally copies every observation tensor to the
+host each step (what a host-side policy would need; PCIe-bound). Prints ONE JSON line (rank 0).
 """
 import argparse
 import ctypes as C
@@ -57,7 +65,10 @@ def parse():
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port (plain C restatement of the reference, pthreads over envs)
+# CPU arms. (1) kind "reference": the UNMODIFIED reference (oracle/_ref, copied from /root/reference by
+# oracle/make_ref.py in the build container) stepped through its own public API on the host cores;
+# (2) the C port of the same step+obs (oracle/wh_oracle.c, pthreads over envs) as the conservative
+# comparator: what a competent native CPU implementation reaches.
 # ------------------------------------------------------------------------------------------------
 def cpu_rollout_rate(variant, n_envs, steps, threads, seed, policy="random", warmup=5):
     import numpy as np
@@ -73,89 +84,92 @@ def cpu_rollout_rate(variant, n_envs, steps, threads, seed, policy="random", war
     return agent_steps / dt, dt, agent_steps
 
 
-def _python_port_worker(job):
-    """One reference-style env object (numpy port of core.py) stepped in a Python loop."""
-    variant, seconds, seed = job
-    import numpy as np
-    from oracle import ref_port as rp
-    from oracle import wh_oracle as wo
-    v = wo.VARIANTS[variant]
-    A = v["num_requests"]
-    env = rp.PortWarehouse(A, v["num_requests"], v["area_dimension"], v["racks"], rng=np.random.default_rng(seed))
-    env.reset()
-    rng = np.random.default_rng(seed + 1)
-    n, t0 = 0, time.perf_counter()
-    while time.perf_counter() - t0 < seconds:
-        for _ in range(50):
-            acts = rng.integers(0, 9, size=A)
-            _, _, done = env.step(list(enumerate(acts.tolist())))
-            n += 1
-            if done:
-                env.reset()
-    return n * A, time.perf_counter() - t0
+def c_port_leg(variant, n_envs, seconds, seed, steps=None):
+    """The C port on every host thread. steps=None: as many steps as fill `seconds` (>= 8)."""
+    from oracle import ref_timing as rt
+    threads = rt.host_cores()
+    if steps is None:
+        rate, _, _ = cpu_rollout_rate(variant, n_envs, 4, threads, seed, "random", warmup=1)
+        steps = min(4000, max(8, int(seconds * rate / (n_envs * VARIANT_AGENTS[variant]))))
+    rate, dt, _ = cpu_rollout_rate(variant, n_envs, steps, threads, seed, "random")
+    return {"value": rate, "unit": "agent-steps/s", "cores": threads, "kind": "port", "seconds": dt,
+            "sample": f"oracle/wh_oracle.c (C port of core.py step+obs, -O3 -march=native), {n_envs} {variant} envs x "
+                      f"{steps} steps, random actions, {threads} pthreads, {dt:.1f}s"}
 
 
-def python_port_baseline(variant, seconds, seed):
-    """The reference's own cost class: Python + numpy, one env object per process (what RLlib's
-    MultiAgentEnv->BaseEnv vectorisation loops over), on every host core."""
-    import multiprocessing as mp
-    cores = os.cpu_count() or 1
-    with mp.get_context("spawn").Pool(cores) as pool:
-        res = pool.map(_python_port_worker, [(variant, seconds, seed + 17 * i) for i in range(cores)])
-    rate = sum(n / dt for n, dt in res)
-    return {"value": rate, "unit": "agent-steps/s", "cores": cores, "kind": "port",
-            "sample": f"oracle/ref_port.py (numpy port at the reference's granularity), 1 {variant} env per process x "
-                      f"{cores} processes, {seconds:.0f}s each, random actions"}
+def reference_legs(variant, steps, warmup, seconds, seed):
+    """The unmodified reference on the host: (a) every core, one process per core, each looping over its
+    own env objects; (b) one process looping over env objects (RLlib's own MultiAgentEnv->BaseEnv
+    vectorisation). The sample (env objects per process) is sized from a short calibration so that
+    `steps` steps fill about `seconds` of wall time; every step is one env.step of every env object."""
+    from oracle import ref_timing as rt
+    cores = rt.host_cores()
+    A = VARIANT_AGENTS[variant]
+    per_env_step = rt.calibrate(variant, seed)
+    n_per_proc = max(1, min(2048, int(round(seconds / (steps * per_env_step)))))
+    agent_steps, dt, procs = rt.time_all_cores(variant, n_per_proc, steps, warmup, seed, cores)
+    allc = {"value": agent_steps / dt, "unit": "agent-steps/s", "cores": procs, "kind": "reference", "seconds": dt,
+            "envs_per_step": n_per_proc * procs, "steps": steps,
+            "sample": f"unmodified reference Warehouse.step (oracle/_ref/warehouse/core.py via its dict API), "
+                      f"{procs} processes x {n_per_proc} {variant} env objects ({n_per_proc * procs} envs per step) x "
+                      f"{steps} steps, random actions, episodes reset when done, {dt:.1f}s"}
+    s_steps = max(3, min(steps, int(round(min(seconds, 3.0) / (n_per_proc * per_env_step)))))
+    a1, dt1 = rt.time_in_process(variant, n_per_proc, s_steps, min(warmup, 3), seed)
+    allc["single_process"] = {
+        "value": a1 / dt1, "unit": "agent-steps/s", "cores": 1, "kind": "reference", "seconds": dt1,
+        "sample": f"one process looping over {n_per_proc} reference env objects x {s_steps} steps "
+                  f"(what RLlib's MultiAgentEnv->BaseEnv vectorisation does per rollout worker), {dt1:.1f}s"}
+    return allc
+
+
+def have_reference():
+    from oracle import make_ref
+    if os.environ.get("WH_BENCH_NO_REF"):      # tests: exercise the port-only fallback
+        return False
+    return make_ref.available() and make_ref.verify()
 
 
 def cpu_baseline(args, budget_s):
-    threads = os.cpu_count() or 1
-    n = args.cpu_envs
-    rate, dt, _ = cpu_rollout_rate(args.variant, n, 4, threads, args.seed, "random", warmup=1)
-    steps = max(8, int(budget_s * rate / (n * VARIANT_AGENTS[args.variant])))
-    steps = min(steps, 4000)
-    rate, dt, agent_steps = cpu_rollout_rate(args.variant, n, steps, threads, args.seed, "random")
-    out = {
-        "value": rate, "unit": "agent-steps/s", "cores": threads, "kind": "port",
-        "sample": f"oracle/wh_oracle.c (C port of core.py step+obs), {n} {args.variant} envs x {steps} steps, "
-                  f"random actions, {threads} pthreads, {dt:.1f}s",
-    }
-    try:
-        out["python_port"] = python_port_baseline(args.variant, 4.0, args.seed)
-    except Exception as e:  # noqa: BLE001
-        out["python_port"] = {"error": repr(e)}
+    """cpu_baseline of the GPU line: bounded samples of the same workload (about budget_s of CPU time)."""
+    if have_reference():
+        out = reference_legs(args.variant, 12, 2, 0.35 * budget_s, args.seed)
+        out["c_port"] = c_port_leg(args.variant, args.cpu_envs, 0.35 * budget_s, args.seed)
+    else:
+        out = c_port_leg(args.variant, args.cpu_envs, 0.7 * budget_s, args.seed)
+        out["note"] = ("oracle/_ref (the copied reference) is absent on this box: run `python oracle/make_ref.py` where "
+                       "/root/reference is mounted; only the C port was timed")
     return out
 
 
 def run_reference(args):
-    """--impl reference: the CPU implementation of the same env.step on all host threads; each
-    step is one env.step over a bounded sample of the workload (args.cpu_envs envs)."""
+    """--impl reference: the reference's own CPU implementation of the path, every host core, on a bounded
+    sample of the config (`cpu_sample_envs_per_step` env objects per step instead of envs_total), sized so
+    that the `--steps` timed steps are a steady-state window of a few seconds whatever --steps is."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import numpy as np
-    from oracle import wh_oracle as wo
-    threads = os.cpu_count() or 1
-    n, A = args.cpu_envs, VARIANT_AGENTS[args.variant]
-    env = wo.OracleEnv(wo.variant_config(args.variant), n, seed=args.seed)
-    env.reset()
-    rng = np.random.Generator(np.random.PCG64(args.seed))
-    actions = rng.integers(0, 9, size=(16, n, env.R)).astype(np.int32)        # 16 distinct action sets, cycled
-    env.rollout(args.warmup, threads, policy="random", actions=actions)
-    t0 = time.perf_counter()
-    agent_steps = env.rollout(args.steps, threads, policy="random", actions=actions)
-    dt = time.perf_counter() - t0
-    rate = agent_steps / dt
-    sample = (f"oracle/wh_oracle.c (C port of the reference step+obs; the Python reference cannot travel to "
-              f"the GPU box), bounded sample: {n} {args.variant} envs per step instead of the config's "
-              f"envs_total, random actions, {threads} pthreads")
+    window_s = max(4.0, args.cpu_seconds / 2)
+    if have_reference():
+        leg = reference_legs(args.variant, args.steps, args.warmup, window_s, args.seed)
+        leg["c_port"] = c_port_leg(args.variant, args.cpu_envs, window_s, args.seed)
+        per_step = leg["envs_per_step"]
+    else:
+        # the C port with exactly --steps steps over a sample sized for a >= window_s region
+        from oracle import ref_timing as rt
+        rate, _, _ = cpu_rollout_rate(args.variant, 2048, 4, rt.host_cores(), args.seed, "random", warmup=1)
+        per_step = int(max(1024, min(1 << 20, window_s * rate / (args.steps * VARIANT_AGENTS[args.variant]))))
+        leg = c_port_leg(args.variant, per_step, window_s, args.seed, steps=args.steps)
+        leg["note"] = "oracle/_ref absent on this box: C port timed instead of the unmodified reference"
+    rate, dt = leg["value"], leg["seconds"]
+    cfg = workload_config(args, max(1, args.gpus))
+    cfg["cpu_sample_envs_per_step"] = per_step
+    cfg["workload"] += f" (CPU arm: bounded sample of {per_step} env objects per step)"
     emit({
         "impl": "reference", "metric": "agent_steps_per_sec", "value": rate, "unit": "agent-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": args.scaling,
-        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": workload_config(args, max(1, args.gpus)),
-        "cpu_baseline": {"value": rate, "unit": "agent-steps/s", "cores": threads, "kind": "port", "sample": sample},
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": cfg,
+        "cpu_baseline": leg,
         "e2e": {"value": rate, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
 
@@ -269,26 +283,51 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # End-of-rollout reduction of the episode statistics (scripts/train.py:18-23 metrics): the repo's own
+    # C-ABI collective, wh_stats_allreduce = ncclAllReduce(sum, 80 x uint64) on a raw ncclComm_t over
+    # NVLink. It is NOT part of a step: it is issued once during warm-up (communicator / channel setup),
+    # and once after the timed steps inside its own CUDA-event pair (`collective_ms`).
+    raw, coll_api = None, "none (single GPU)"
+    if world > 1:
+        try:
+            from rllib_warehouse_b200.parallel import RawNcclStats
+            raw = RawNcclStats(dev)
+            coll_api = "wh_stats_allreduce (C ABI, raw ncclComm_t, ncclAllReduce sum of 80 uint64)"
+        except Exception as e:  # noqa: BLE001
+            coll_api = f"torch.distributed.all_reduce (raw communicator unavailable: {e!r})"
+
+    def reduce_stats():
+        if world == 1:
+            return env.stats.clone()
+        if raw is not None:
+            return raw.allreduce(env.stats)
+        out = env.stats.clone()
+        dist.all_reduce(out)
+        return out
+
     for i in range(args.warmup):
         one_step(i)
+    reduce_stats()                           # warm the collective (same dtype / count / stream)
     barrier()
     launches0 = env.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evc0, evc1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
         ev0.record()
         for i in range(args.steps):
             one_step(i)
-        stats = env.stats.clone()
-        if world > 1:
-            dist.all_reduce(stats)           # end-of-rollout episode statistics over NCCL
-        ev1.record()
+        ev1.record()                         # right after the last k_step of the K timed steps
+        gpu_launches = env.launches - launches0
+        evc0.record()
+        stats = reduce_stats()               # end-of-rollout episode statistics over NCCL
+        evc1.record()
         barrier()
-    gpu_launches = env.launches - launches0
     ms = ev0.elapsed_time(ev1)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    coll_ms = evc0.elapsed_time(evc1)
+    t = torch.tensor([ms, coll_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms, coll_ms = float(t[0].item()), float(t[1].item())
     value = n_total * A * args.steps / (ms * 1e-3)
 
     # ---- dominant kernel (fused step+obs) timed per launch with CUDA events on its stream ----
@@ -322,16 +361,18 @@ def run_b200(args):
         peak = 6650.0
     alg_bytes = ALG_BYTES_PER_ENV_STEP[args.variant] * n_local
     achieved = alg_bytes / (k_avg_ms * 1e-3) / 1e9
-    traffic = None
-    try:   # ncu-measured DRAM bytes per launch for this exact launch shape (profiles/, round 1)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[args.variant]
-        if tj["envs_per_launch"] == n_local:
-            traffic = tj["traffic_bytes"]
-    except Exception:  # noqa: BLE001
-        pass
+    traffic, traffic_src = None, None
+    for fn in ("r02_traffic.json", "r01_traffic.json"):
+        try:   # ncu DRAM bytes per launch of this exact launch shape, from the committed capture (static, not re-measured in this run)
+            tj = json.load(open(os.path.join(ROOT, "profiles", fn)))[args.variant]
+            if tj["envs_per_launch"] == n_local:
+                traffic, traffic_src = tj["traffic_bytes"], f"profiles/{fn} (static: ncu --set full capture of this launch shape, dram__bytes_read.sum + dram__bytes_write.sum)"
+                break
+        except Exception:  # noqa: BLE001
+            pass
     roofline = {
         "bound": "hbm", "kernel": "wh::k_step (fused step + observation build)", "achieved": achieved,
-        "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+        "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
         "alg_bytes_per_launch": alg_bytes, "kernel_ms_avg": k_avg_ms,
         "kernel_ms_source": ("timed region (CUDA events) / launches in it" if launches_per_step == 1
                              else "one CUDA-event pair per launch"),
@@ -346,15 +387,23 @@ def run_b200(args):
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "int32",
         "data": "synthetic", "config": workload_config(args, world),
         "roofline": roofline, "gpu_launches": gpu_launches, "launches_per_step": launches_per_step,
+        "collective_ms": coll_ms, "collective_api": coll_api,
         "clocks": clocks.summary(),
     }
 
-    # ---- e2e through the host-buffer C ABI: pinned actions in, rewards + dones out, every step ----
+    # ---- e2e through the host-buffer C ABI (wh_env_step_host*): HOST buffers in and out, every step ----
+    # Three consumers are modelled, all through the same public entry point:
+    #   e2e          int32 actions in / float32 rewards + uint8 dones out (the reference's dtypes); the
+    #                observations stay in HBM, i.e. an ON-DEVICE policy reads them there (wh_env_obs_ptrs);
+    #   e2e_alt      the same with int8 / uint8 on the wire (lossless: actions 0..8, rewards 0/1/2);
+    #   e2e_host_obs what `env.step` itself returns to a HOST policy: all eight observation tensors are
+    #                copied device->host every step as well (2.2 GB per step for Large: PCIe-bound).
     if not args.no_e2e:
         L = nv.lib()
         ccfg = nv.make_config(cfg)
 
-        def run_e2e(compact, chunks):
+        def run_e2e(mode, chunks, steps):
+            compact, host_obs = mode == "compact", mode == "host_obs"
             h = C.c_void_p()
             nv.check(L.wh_env_create(C.byref(ccfg), n_local, local, rank * n_local, args.seed, chunks,
                                      C.byref(h)), "wh_env_create")
@@ -363,6 +412,11 @@ def run_b200(args):
             host_actions = [torch.randint(0, 9, (n_local, R), dtype=adt).pin_memory() for _ in range(4)]
             host_rewards = torch.zeros((n_local, R), dtype=rdt).pin_memory()
             host_dones = torch.zeros(n_local, dtype=torch.uint8).pin_memory()
+            obs_bytes, obs_struct, keep = 0, None, None
+            if host_obs:
+                keep = {k: torch.empty(tuple(env.obs[k].shape), dtype=env.obs[k].dtype).pin_memory() for k in nv.OBS_KEYS}
+                obs_struct = nv.Obs(**{k: keep[k].data_ptr() for k in nv.OBS_KEYS})
+                obs_bytes = sum(t.numel() * t.element_size() for t in keep.values())
 
             def call(i):
                 if compact:
@@ -370,14 +424,14 @@ def run_b200(args):
                                                     host_dones.data_ptr())
                 else:
                     rc = L.wh_env_step_host(h, host_actions[i & 3].data_ptr(), host_rewards.data_ptr(),
-                                            host_dones.data_ptr(), None)
+                                            host_dones.data_ptr(), C.byref(obs_struct) if host_obs else None)
                 nv.check(rc, "wh_env_step_host")
 
-            for i in range(5):
+            for i in range(3 if host_obs else 5):
                 call(i)
             barrier()
             t0 = time.perf_counter()
-            for i in range(args.e2e_steps):
+            for i in range(steps):
                 call(i)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
@@ -386,24 +440,33 @@ def run_b200(args):
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = float(tt.item())
             launches = int(L.wh_env_launch_count(h))
+            api = {"ref_dtypes": "wh_env_step_host: int32 actions in, float32 rewards + uint8 dones out (the reference's dtypes); "
+                                 "observations stay in HBM for an on-device policy (wh_env_obs_ptrs)",
+                   "compact": "wh_env_step_host_compact: int8 actions in, uint8 rewards + dones out (lossless narrow wire format); "
+                              "observations stay in HBM for an on-device policy",
+                   "host_obs": "wh_env_step_host with obs_host: everything env.step returns goes to the host every step "
+                               "(all 8 observation tensors + rewards + dones), for a host-side policy; PCIe-bound"}[mode]
             res = {
-                "value": n_total * A * args.e2e_steps / dt, "unit": "agent-steps/s",
+                "value": n_total * A * steps / dt, "unit": "agent-steps/s",
                 "h2d_bytes_per_step": n_local * R * host_actions[0].element_size(),
-                "d2h_bytes_per_step": n_local * R * host_rewards.element_size() + n_local,
-                "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps, "chunks": chunks,
-                "api": ("wh_env_step_host_compact (int8 actions / uint8 rewards on the wire)" if compact else
-                        "wh_env_step_host (int32 actions / float32 rewards, the reference's dtypes)")
-                       + "; C ABI, pinned host buffers, observations stay in HBM",
+                "d2h_bytes_per_step": n_local * R * host_rewards.element_size() + n_local + obs_bytes,
+                "steps": steps, "ms_per_step": 1e3 * dt / steps, "chunks": chunks,
+                "api": api + "; C ABI, pinned host buffers",
                 "reward_checksum": float(host_rewards.sum()), "gpu_launches": launches,
             }
+            if host_obs:
+                res["d2h_GBps"] = res["d2h_bytes_per_step"] / (dt / steps) / 1e9
+                res["obs_checksum"] = int(keep["requests"].sum())
             L.wh_env_destroy(h)
             return res
 
-        ref_dtypes = run_e2e(False, args.e2e_chunks)
-        compact = run_e2e(True, args.e2e_chunks)
-        best, other = (compact, ref_dtypes) if compact["value"] >= ref_dtypes["value"] else (ref_dtypes, compact)
-        out["e2e"] = best
-        out["e2e_alt"] = other
+        out["e2e"] = run_e2e("ref_dtypes", args.e2e_chunks, args.e2e_steps)
+        out["e2e_alt"] = run_e2e("compact", args.e2e_chunks, args.e2e_steps)
+        if world == 1:
+            try:
+                out["e2e_host_obs"] = run_e2e("host_obs", args.e2e_chunks, max(4, args.e2e_steps // 10))
+            except Exception as e:  # noqa: BLE001
+                out["e2e_host_obs"] = {"error": repr(e)}
     if world == 1 and not args.no_extras:
         out["extras"] = extras(args, dev, peak)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -412,6 +475,8 @@ def run_b200(args):
     if rank == 0:
         emit(out)
     if world > 1:
+        if raw is not None:
+            raw.close()
         dist.barrier()
         dist.destroy_process_group()
 

@@ -139,7 +139,8 @@ int wh_build_obs_flat(const wh_config *cfg, const wh_state *st, int64_t n_envs, 
 
 /* WarehouseRandomGreedySolver.compute_action — solvers.py:27-58 — on observation tensors.
  * rand_threshold = floor(random_action_prob * 2^32). is_random / random_actions [N,R] replay the
- * eps-random branch (solvers.py:44-45); NULL = native RNG keyed by (seed, env, episode, time, agent).
+ * eps-random branch (solvers.py:44-45); NULL = native RNG keyed by (seed, env, episode, time,
+ * agent | 0x80000000 — a stream separate from the env's respawn draws even for equal seeds).
  * actions [N,R] int32 out (-1 for rows >= num_agents). */
 int wh_greedy(const wh_config *cfg, const wh_obs *obs, const int8_t *num_agents,
               const int32_t *episode, const int32_t *time, int64_t n_envs, int64_t env_id0,
@@ -171,8 +172,10 @@ int wh_stats_allreduce(unsigned long long *stats, void *nccl_comm, void *stream)
 /* ---- Layer 2: host-buffer environment handle -------------------------------------------- */
 typedef struct wh_env wh_env;
 
-/* Allocates device state + observation tensors for n_envs on `device`, pinned staging and
- * `n_chunks` streams. keep_obs_on_device = 1 leaves observations in HBM (wh_env_obs_ptrs). */
+/* Allocates device state + observation tensors for n_envs on `device` and `n_chunks` streams (the
+ * env batch is processed as n_chunks copy -> kernel -> copy pipelines). Observations always stay
+ * resident in HBM (wh_env_obs_ptrs); wh_env_step_host copies them out only when given obs_host.
+ * On failure nothing is left allocated and *out is NULL. */
 int wh_env_create(const wh_config *cfg, int64_t n_envs, int device, int64_t env_id0, uint64_t seed,
                   int n_chunks, wh_env **out);
 void wh_env_destroy(wh_env *env);

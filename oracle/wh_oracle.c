@@ -408,7 +408,9 @@ static void greedy_one(const who_config *cfg, const who_obs *o, const int32_t *n
             if (is_random[row]) action = random_actions[row];
         } else if (thr) {
             uint32_t rnd[4];
-            who_philox((uint32_t)env_id, (uint32_t)episode[e], (uint32_t)time[e], (uint32_t)i, seed, rnd);
+            /* solver stream: agent index tagged with bit 31, so it never shares a counter with the env's
+             * respawn draws of the same (env, episode, time) even when solver_seed == seed */
+            who_philox((uint32_t)env_id, (uint32_t)episode[e], (uint32_t)time[e], (uint32_t)i | 0x80000000u, seed, rnd);
             if ((uint64_t)rnd[0] < thr) action = (int)bounded(rnd[1], 9);
         }
         actions[row] = action;

@@ -4,7 +4,9 @@ Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl refer
 import this module; the product package (rllib_warehouse_b200) must never do so.
 """
 import ctypes as C
+import hashlib
 import os
+import re
 import subprocess
 
 import numpy as np
@@ -46,11 +48,27 @@ VARIANTS = {
 }
 
 
+def _host_tag():
+    """Identifies the CPU the library was compiled for: it is built with -march=native, and the
+    build container's .so travels to the GPU box, whose host may be a different CPU."""
+    try:
+        txt = open("/proc/cpuinfo").read()
+        model = re.search(r"model name\s*:\s*(.*)", txt)
+        flags = re.search(r"flags\s*:\s*(.*)", txt)
+        return (model.group(1) if model else "?") + " | " + hashlib.sha1((flags.group(1) if flags else "").encode()).hexdigest()
+    except OSError:
+        return "unknown"
+
+
 def build(force=False):
-    if force or not os.path.exists(LIB_PATH) or (
-        os.path.getmtime(LIB_PATH) < os.path.getmtime(os.path.join(HERE, "wh_oracle.c"))
-    ):
+    tag_path, tag = LIB_PATH + ".host", _host_tag()
+    stale = (not os.path.exists(LIB_PATH)
+             or os.path.getmtime(LIB_PATH) < os.path.getmtime(os.path.join(HERE, "wh_oracle.c"))
+             or not os.path.exists(tag_path) or open(tag_path).read() != tag)
+    if force or stale:
         subprocess.check_call(["make", "-C", HERE, "-s", "-B"], env={**os.environ, "CC": "gcc"})
+        with open(tag_path, "w") as f:
+            f.write(tag)
     return LIB_PATH
 
 

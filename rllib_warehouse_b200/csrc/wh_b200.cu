@@ -1,5 +1,6 @@
 // wh_b200.cu — kernels' __global__ entry points, launch dispatch and the C ABI (include/wh_b200.h).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -9,7 +10,7 @@
 
 #include "wh_kernels.cuh"
 #ifdef WH_WITH_TPE
-#include "experimental/wh_tpe.cuh"   // thread-per-env kernels: bit-exact but slower, see the file header
+#include "../../tools/experimental/wh_tpe.cuh"   // rejected thread-per-env experiment (kept with the tuning tools, not in the product tree)
 #endif
 
 namespace wh {
@@ -313,7 +314,7 @@ __global__ void __launch_bounds__(BLOCK) k_greedy(const __grid_constant__ KParam
     } else if (P.rand_thr) {
         uint32_t u0, u1;
         philox4x32_10((uint32_t)(P.env_id0 + e), (uint32_t)P.g_episode[e], (uint32_t)P.g_time[e],
-                      (uint32_t)a, P.solver_seed, u0, u1);
+                      (uint32_t)a | CTR_SOLVER_TAG, P.solver_seed, u0, u1);
         if ((unsigned long long)u0 < P.rand_thr) action = (int)bounded(u1, 9u);
     }
     if (live && j == 0) P.actions_out[row] = (a < A) ? action : -1;
@@ -404,15 +405,15 @@ static void launch_kind(Kind kind, const KParams &K, cudaStream_t s) {
     // faster than what the register count alone would allow (Large: 3 blocks, profiles/README.md)
     const size_t dyn = RC == 16 ? WH_LARGE_DYN_SMEM : 0;
     if (dyn) {   // static + dynamic > 48 KB needs the opt-in, once per device (function attributes are per device)
-        static bool done[64] = {};
+        static std::atomic<bool> done[64];   // setting the attribute twice is harmless: a flag per device is enough
         int dev = 0;
         cudaGetDevice(&dev);
-        if (dev >= 0 && dev < 64 && !done[dev]) {
+        if (dev >= 0 && dev < 64 && !done[dev].load(std::memory_order_acquire)) {
             cudaFuncSetAttribute(k_step<GC, RC, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
             cudaFuncSetAttribute(k_step<GC, RC, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
             cudaFuncSetAttribute(k_step<GC, RC, false, false, RC != 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
             cudaFuncSetAttribute(k_step<GC, RC, true, false, RC != 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-            done[dev] = true;
+            done[dev].store(true, std::memory_order_release);
         }
     }
     const bool plain = RC != 0 && !(K.flags & WH_FLAG_COMPACT_IO) && !K.order && !K.spawn_p;
@@ -442,7 +443,7 @@ static void launch_greedy(const KParams &K, cudaStream_t s) {
 }
 
 #ifdef WH_WITH_TPE
-// Thread-per-environment kernels (experimental/wh_tpe.cuh) for the default path of Small / Medium.
+// Thread-per-environment kernels (tools/experimental/wh_tpe.cuh) for the default path of Small / Medium.
 template <int RC>
 static void launch_tpe(Kind kind, const KParams &K, cudaStream_t s) {
     constexpr int WARPS = 4;
@@ -654,6 +655,8 @@ int wh_stats_allreduce(unsigned long long *stats, void *nccl_comm, void *stream)
 // ---------------------------------------------------------------------------------------------
 // C ABI — layer 2: host-buffer environment handle
 // ---------------------------------------------------------------------------------------------
+void wh_env_destroy(wh_env *E);
+
 struct wh_env {
     wh_config cfg;
     int64_t N, env_id0;
@@ -687,22 +690,8 @@ static wh_obs offset_obs(const wh_obs &b, int64_t e0, int64_t R) {
     return o;
 }
 
-int wh_env_create(const wh_config *cfg, int64_t n_envs, int device, int64_t env_id0, uint64_t seed,
-                  int n_chunks, wh_env **out) {
-    if (!cfg || !out || n_envs <= 0) return WH_E_ARG;
-    KParams K; Shape sh;
-    if (int rc = fill_params(cfg, K, sh)) return rc;
-    if (n_envs == 0) return 0;   // empty batch: nothing to launch
-    CK(cudaSetDevice(device));
-    wh_env *E = new (std::nothrow) wh_env();
-    if (!E) return WH_E_ARG;
-    memset(E, 0, sizeof(*E));
-    E->cfg = *cfg; E->N = n_envs; E->env_id0 = env_id0; E->seed = seed; E->device = device;
-    E->R = K.R; E->P = K.P;
-    if (n_chunks < 1) n_chunks = 1;
-    if (n_chunks > 64) n_chunks = 64;
-    E->n_chunks = n_chunks;
-    const int64_t N = n_envs, R = K.R, P = K.P;
+static int env_alloc(wh_env *E, const KParams &K, int n_chunks) {
+    const int64_t N = E->N, R = K.R, P = K.P;
     CK(cudaMalloc(&E->st.agent_pos, N * R * 2)); CK(cudaMalloc(&E->st.agent_tgt, N * R));
     CK(cudaMalloc(&E->st.pickup_tgt, N * P)); CK(cudaMalloc(&E->st.pickup_timer, N * P * 2));
     CK(cudaMalloc(&E->st.time, N * 4)); CK(cudaMalloc(&E->st.num_agents, N));
@@ -721,8 +710,31 @@ int wh_env_create(const wh_config *cfg, int64_t n_envs, int device, int64_t env_
     CK(cudaMalloc(&E->d_dones, N)); CK(cudaMalloc(&E->d_stats, WH_NUM_STATS * 8));
     CK(cudaMemset(E->d_stats, 0, WH_NUM_STATS * 8));
     E->streams = (cudaStream_t *)calloc((size_t)n_chunks, sizeof(cudaStream_t));
+    if (!E->streams) return WH_E_ARG;
     for (int i = 0; i < n_chunks; ++i) CK(cudaStreamCreateWithFlags(&E->streams[i], cudaStreamNonBlocking));
     CK(cudaDeviceSynchronize());
+    return 0;
+}
+
+int wh_env_create(const wh_config *cfg, int64_t n_envs, int device, int64_t env_id0, uint64_t seed,
+                  int n_chunks, wh_env **out) {
+    if (!cfg || !out || n_envs <= 0) return WH_E_ARG;
+    *out = nullptr;
+    KParams K; Shape sh;
+    if (int rc = fill_params(cfg, K, sh)) return rc;
+    CK(cudaSetDevice(device));
+    wh_env *E = new (std::nothrow) wh_env();
+    if (!E) return WH_E_ARG;
+    memset(E, 0, sizeof(*E));
+    E->cfg = *cfg; E->N = n_envs; E->env_id0 = env_id0; E->seed = seed; E->device = device;
+    E->R = K.R; E->P = K.P;
+    if (n_chunks < 1) n_chunks = 1;
+    if (n_chunks > 64) n_chunks = 64;
+    E->n_chunks = n_chunks;
+    if (int rc = env_alloc(E, K, n_chunks)) {   // a failed allocation leaves nothing behind
+        wh_env_destroy(E);
+        return rc;
+    }
     *out = E;
     return 0;
 }
@@ -755,9 +767,8 @@ int wh_env_reset(wh_env *E) {
     return 0;
 }
 
-static int env_step_impl(wh_env *E, const int32_t *actions, float *rewards, uint8_t *dones,
-                         const wh_obs *obs_host, bool greedy, bool compact = false) {
-    if (!E || !rewards || !dones || (!greedy && !actions)) return WH_E_ARG;
+static int env_step_issue(wh_env *E, const int32_t *actions, float *rewards, uint8_t *dones,
+                         const wh_obs *obs_host, bool greedy, bool compact) {
     CK(cudaSetDevice(E->device));
     const int64_t R = E->R;
     for (int c = 0; c < E->n_chunks; ++c) {
@@ -805,8 +816,20 @@ static int env_step_impl(wh_env *E, const int32_t *actions, float *rewards, uint
             CK(cudaMemcpyAsync(oh.requests, ob.requests, n * R * R * 16, cudaMemcpyDeviceToHost, s));
         }
     }
-    for (int c = 0; c < E->n_chunks; ++c) CK(cudaStreamSynchronize(E->streams[c]));
     return 0;
+}
+
+// Issues the per-chunk copy -> kernel -> copy pipelines, then ALWAYS drains every chunk stream — also when
+// issuing failed half-way — so that no copy into the caller's host buffers is still in flight on return.
+static int env_step_impl(wh_env *E, const int32_t *actions, float *rewards, uint8_t *dones,
+                         const wh_obs *obs_host, bool greedy, bool compact = false) {
+    if (!E || !rewards || !dones || (!greedy && !actions)) return WH_E_ARG;
+    int rc = env_step_issue(E, actions, rewards, dones, obs_host, greedy, compact);
+    for (int c = 0; c < E->n_chunks; ++c) {
+        const cudaError_t e = cudaStreamSynchronize(E->streams[c]);
+        if (!rc && e != cudaSuccess) rc = (int)e;
+    }
+    return rc;
 }
 
 int wh_env_step_host(wh_env *E, const int32_t *actions, float *rewards, uint8_t *dones,

@@ -43,6 +43,9 @@ constexpr uint32_t NO_CELL = 0xffff0000u;  // never equals a packed 16-bit cell
 constexpr uint32_t CTR_NUM_AGENTS = 0xFFFFFFFFu;
 constexpr uint32_t CTR_SPAWN_AGENT = 0xF0000000u;
 constexpr uint32_t CTR_INIT_REQUESTS = 0xE0000000u;
+// The solver's eps-random draws use the same (env, episode, time) counter words as the env's respawn
+// draws; bit 31 of the lane word separates the two streams even when solver_seed == seed.
+constexpr uint32_t CTR_SOLVER_TAG = 0x80000000u;
 
 struct KParams {
     // geometry (core.py:92-108, variants.py)
@@ -999,7 +1002,7 @@ __device__ __forceinline__ int greedy_from_state(const KParams &P, const Group<G
     int action = (sx + 1) * 3 + (sy + 1);                                      // solvers.py:47-49
     if (P.rand_thr) {                                                          // solvers.py:44-45
         uint32_t u0, u1;
-        philox4x32_10(env_id, (uint32_t)s.ep, (uint32_t)s.time, (uint32_t)g.gl, P.solver_seed, u0, u1);
+        philox4x32_10(env_id, (uint32_t)s.ep, (uint32_t)s.time, (uint32_t)g.gl | CTR_SOLVER_TAG, P.solver_seed, u0, u1);
         if ((unsigned long long)u0 < P.rand_thr) action = (int)bounded(u1, 9u);
     }
     return (g.gl < s.A) ? action : -1;

@@ -8,9 +8,11 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_reference_arm_json_line():
+def _reference_line(extra_env=None):
+    env = dict(os.environ, **(extra_env or {}))
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "3",
-                          "--warmup", "1", "--cpu-envs", "256"], capture_output=True, text=True, timeout=300)
+                          "--warmup", "1", "--cpu-envs", "256", "--cpu-seconds", "2"], capture_output=True, text=True,
+                         timeout=600, env=env)
     assert res.returncode == 0, res.stderr[-2000:]
     lines = [l for l in res.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
@@ -18,8 +20,33 @@ def test_reference_arm_json_line():
     assert d["impl"] == "reference" and d["metric"] == "agent_steps_per_sec" and d["unit"] == "agent-steps/s"
     assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["value"] > 0
     assert d["config"]["workload"].startswith("warehouse-large-262144") and d["config"]["envs_per_gpu"] == 262144
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    # the bounded CPU sample is stated, not hidden behind the config's 262 144 envs
+    assert d["config"]["cpu_sample_envs_per_step"] >= 1 and "bounded sample" in d["config"]["workload"]
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    return d
+
+
+def test_reference_arm_json_line():
+    """With oracle/_ref present (made by oracle/make_ref.py where the reference is mounted) the arm times
+    the UNMODIFIED reference: kind "reference", single-process and C-port legs beside it."""
+    sys.path.insert(0, ROOT)
+    from oracle import make_ref
+    if not make_ref.available():
+        if make_ref.make() is None:
+            import pytest
+            pytest.skip("neither /root/reference nor oracle/_ref on this box")
+    assert make_ref.verify()
+    d = _reference_line()
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "reference" and "unmodified reference" in cb["sample"]
+    assert cb["single_process"]["kind"] == "reference" and cb["single_process"]["cores"] == 1
+    assert cb["c_port"]["kind"] == "port" and cb["c_port"]["value"] > cb["value"]     # C beats Python + numpy
+
+
+def test_reference_arm_without_the_reference_copy():
+    d = _reference_line({"WH_BENCH_NO_REF": "1"})
+    assert d["cpu_baseline"]["kind"] == "port" and "absent" in d["cpu_baseline"]["note"]
 
 
 def test_reference_arm_other_ranks_exit_quietly():

@@ -23,7 +23,7 @@
 // auto-reset, compact I/O, in-kernel greedy solver. Everything else (custom order, replayed draws,
 // flattened observations, runtime geometry) stays on the lane-group kernels.
 #pragma once
-#include "../wh_kernels.cuh"
+#include "../../rllib_warehouse_b200/csrc/wh_kernels.cuh"
 
 namespace wh {
 
