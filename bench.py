@@ -514,6 +514,7 @@ def extras(args, dev, peak):
         rnd = torch.randint(0, 9, (n, env.R), dtype=torch.int32, device=dev)
         ms_flat = _time_steps(lambda i: env.step_flat(rnd), steps, warm)
         ms_roll = _time_steps(lambda i: env.greedy_rollout(50, with_obs=False), 6, 2) / 50
+        ms_multi = _time_steps(lambda i: env.multi_step(50), 6, 2) / 50
         sb = SOLVER_BYTES_PER_AGENT[variant] * n * A
         fb = ALG_BYTES_PER_ENV_STEP[variant] * n
         res[name] = {
@@ -526,6 +527,11 @@ def extras(args, dev, peak):
             # state in registers, NO observations written — a different (lighter) operation than env.step
             "greedy_rollout_kernel_no_obs": {"ms_per_step": ms_roll, "agent_steps_per_sec": n * A / (ms_roll * 1e-3),
                                              "steps_per_launch": 50},
+            # wh_multi_step: 50 greedy solver+step iterations per launch, the state in registers, EVERY step's
+            # observations / rewards / dones written (same bytes per step as fused_greedy_step; no per-step
+            # launch ramp / tail)
+            "multi_step_greedy_obs_every_step": {"ms_per_step": ms_multi, "agent_steps_per_sec": n * A / (ms_multi * 1e-3),
+                                                 "frac": fb / ms_multi / 1e6 / peak, "steps_per_launch": 50},
             # RLlib-flattened float32 observations from the step kernel: 4(9R+1) B/agent instead of 33R+4
             "step_flat_f32_obs": {"ms": ms_flat, "agent_steps_per_sec": n * A / (ms_flat * 1e-3),
                                   "alg_bytes_per_launch": fb + n * A * (4 * (9 * A + 1) - (33 * A + 4)),
@@ -568,7 +574,22 @@ def extras(args, dev, peak):
     ms_eager = _time_steps(lambda i: env.greedy_step(want_actions=False), 400, 20)
     graph = StepGraph(env, steps=50, policy="greedy")
     ms_graph = _time_steps(lambda i: graph.replay(), 20, 3) / 50
+    ms_multi = _time_steps(lambda i: env.multi_step(200), 10, 2) / 200
+    acts = torch.randint(0, 9, (200, 4096, 4), dtype=torch.int32, device=dev)
+    outs = env.multi_step(200, actions=acts, per_step=True)
+    ms_multi_ol = _time_steps(lambda i: env.multi_step(200, actions=acts, per_step=True, out=outs), 10, 2) / 200
+    small_bytes = ALG_BYTES_PER_ENV_STEP["small"] * 4096
     res["configs1_small_4096"] = {
+        # one launch = one whole 200-step episode of all 4 096 envs, observations written every step
+        "multi_step_greedy_200_steps_per_launch": {
+            "ms_per_step": ms_multi, "agent_steps_per_sec": 4096 * 4 / (ms_multi * 1e-3),
+            "frac": small_bytes / ms_multi / 1e6 / peak,
+            "note": "fraction of the HBM copy peak on the algorithmic bytes; the 2.9 MB working set is L2-resident "
+                    "(observations overwrite the resident tensors), so the bound here is latency per step, not HBM"},
+        "multi_step_open_loop_actions_per_step_outputs": {
+            "ms_per_step": ms_multi_ol, "agent_steps_per_sec": 4096 * 4 / (ms_multi_ol * 1e-3),
+            "frac": small_bytes / ms_multi_ol / 1e6 / peak,
+            "note": "random [200,N,R] action tensor in, [200,N,...] observations / rewards / dones out (446 MB per launch: streams to HBM)"},
         "fused_greedy_step_eager": {"ms": ms_eager, "agent_steps_per_sec": 4096 * 4 / (ms_eager * 1e-3)},
         "fused_greedy_step_cuda_graph": {"ms": ms_graph, "agent_steps_per_sec": 4096 * 4 / (ms_graph * 1e-3),
                                          "frac": ALG_BYTES_PER_ENV_STEP["small"] * 4096 / ms_graph / 1e6 / peak,

@@ -91,6 +91,9 @@ typedef struct wh_obs {
                                   while they drain (it touches no memory before they complete); callers
                                   that put copies between the launches gain nothing from it */
 
+#define WH_FLAG_PER_STEP_OUT 8  /* wh_multi_step: rewards / dones / observations are [T, N, ...] tensors and step t
+                                  writes slice t (otherwise: reward sums, last dones, observations overwritten) */
+
 /* stats vector (unsigned 64-bit counters, device memory, WH_NUM_STATS entries):
  * [0] episodes [1] return_sum [2] pickups [3] deliveries [4] expired [5..7] reserved
  * [8+2(n-1)] episodes with n agents, [9+2(n-1)] their return sum  (scripts/train.py:18-23) */
@@ -162,6 +165,23 @@ int wh_greedy_step(const wh_config *cfg, const wh_state *st, int64_t n_envs, int
 int wh_greedy_rollout(const wh_config *cfg, const wh_state *st, int64_t n_envs, int64_t env_id0,
                       uint64_t seed, uint64_t solver_seed, uint64_t rand_threshold, int n_steps,
                       float *reward_sums, uint8_t *dones, unsigned long long *stats, int flags, void *stream);
+
+/* `n_steps` consecutive Warehouse.step calls (core.py:262-442) in ONE launch, the state held in registers
+ * between the steps; every step writes what a single wh_step / wh_greedy_step launch writes. For batch
+ * sizes where one step is shorter than a kernel launch (BASELINE configs[1]: 4 096 Small envs) and for
+ * open-loop replays (recorded / random action tensors, the greedy baseline).
+ *   actions  int32 [n_steps, N, R] open-loop actions (-1 = absent), or NULL = the in-kernel greedy solver
+ *            (solvers.py:27-58; solver_seed / rand_threshold as in wh_greedy_step);
+ *   flags    WH_FLAG_AUTO_RESET, WH_FLAG_PER_STEP_OUT;
+ *   rewards  f32 [n_steps,N,R] / dones u8 [n_steps,N] with WH_FLAG_PER_STEP_OUT, else [N,R] per-agent
+ *            reward SUMS over the steps and [N] the last step's dones;
+ *   obs      NULL = no observations; otherwise written EVERY step: into slice t of [n_steps,N,...] tensors
+ *            with WH_FLAG_PER_STEP_OUT, else over the same [N,...] tensors (what n_steps launches leave).
+ * Moves are resolved in ascending agent order (core.py:279 default); native RNG only. */
+int wh_multi_step(const wh_config *cfg, const wh_state *st, int64_t n_envs, int64_t env_id0, uint64_t seed,
+                  int n_steps, const int32_t *actions, uint64_t solver_seed, uint64_t rand_threshold,
+                  float *rewards, uint8_t *dones, unsigned long long *stats, const wh_obs *obs, int flags,
+                  void *stream);
 
 /* End-of-rollout reduction of the episode statistics over NVLink: in-place ncclAllReduce(sum) of the
  * WH_NUM_STATS uint64 counters on `stream`. `nccl_comm` is a ncclComm_t created by the caller with

@@ -12,6 +12,7 @@ OBS_STEP, OBS_RESET = 0, 1
 FLAG_AUTO_RESET = 1
 FLAG_COMPACT_IO = 2
 FLAG_NO_PDL = 4
+FLAG_PER_STEP_OUT = 8
 
 OBS_KEYS = (
     "num_agents", "self_position", "self_availability", "self_delivery_target",
@@ -22,7 +23,7 @@ STATE_KEYS = ("agent_pos", "agent_tgt", "pickup_tgt", "pickup_timer", "time", "n
 # every symbol include/wh_b200.h declares
 SYMBOLS = (
     "wh_version", "wh_error_string", "wh_num_pickup_points", "wh_num_delivery_points",
-    "wh_reset", "wh_step", "wh_step_flat", "wh_build_obs", "wh_build_obs_flat", "wh_greedy", "wh_greedy_step", "wh_greedy_rollout", "wh_stats_allreduce",
+    "wh_reset", "wh_step", "wh_step_flat", "wh_build_obs", "wh_build_obs_flat", "wh_greedy", "wh_greedy_step", "wh_greedy_rollout", "wh_multi_step", "wh_stats_allreduce",
     "wh_env_create", "wh_env_destroy", "wh_env_reset", "wh_env_step_host", "wh_env_step_host_compact", "wh_env_greedy_step_host",
     "wh_env_obs_ptrs", "wh_env_state_ptrs", "wh_env_stats_host", "wh_env_launch_count",
 )
@@ -69,6 +70,7 @@ def lib():
         L.wh_step_flat.argtypes = [vp, vp, i64, i64, u64, vp, vp, vp, vp, vp, vp, ci, vp]
         L.wh_greedy_step.argtypes = [vp, vp, i64, i64, u64, u64, u64, vp, vp, vp, vp, vp, ci, vp]
         L.wh_greedy_rollout.argtypes = [vp, vp, i64, i64, u64, u64, u64, ci, vp, vp, vp, ci, vp]
+        L.wh_multi_step.argtypes = [vp, vp, i64, i64, u64, ci, vp, u64, u64, vp, vp, vp, vp, ci, vp]
         L.wh_build_obs.argtypes = [vp, vp, i64, ci, vp, vp]
         L.wh_build_obs_flat.argtypes = [vp, vp, i64, ci, vp, vp]
         L.wh_greedy.argtypes = [vp, vp, vp, vp, vp, i64, i64, u64, u64, vp, vp, vp, vp]

@@ -253,6 +253,42 @@ class BatchedWarehouse:
             self.build_obs(nv.OBS_STEP)
         return self.rewards
 
+    def multi_step(self, steps: int, actions=None, random_action_prob=0.0, solver_seed=0, with_obs=True,
+                   per_step=False, out=None):
+        """`steps` consecutive `env.step` calls in ONE kernel launch (wh_multi_step); the state stays in
+        registers between them. actions: int [steps, N, R] open-loop actions, or None = the in-kernel greedy
+        solver (one run.py:42-62 iteration per step). Every step's observations are written (with_obs).
+
+        per_step=False: observations land in the resident tensors (each step overwrites the previous one,
+        exactly what `steps` single launches leave behind); returns (obs, reward SUMS [N,R], last dones [N]).
+        per_step=True: returns per-step tensors — obs dict of [steps, N, ...], rewards [steps, N, R],
+        dones [steps, N] (allocated here, or pass `out=(obs_dict, rewards, dones)` to reuse buffers)."""
+        dev, N, R, T = self.device, self.N, self.R, int(steps)
+        if actions is not None:
+            actions = _dev_tensor(actions, torch.int32, dev, (T, N, R))
+        thr = int(float(random_action_prob) * 4294967296.0)
+        flags = nv.FLAG_AUTO_RESET if self.auto_reset else 0
+        if per_step:
+            flags |= nv.FLAG_PER_STEP_OUT
+            if out is None:
+                obs = ({k: torch.empty((T,) + tuple(v.shape), dtype=v.dtype, device=dev) for k, v in self.obs.items()}
+                       if with_obs else None)
+                out = (obs, torch.empty((T, N, R), dtype=torch.float32, device=dev),
+                       torch.empty((T, N), dtype=torch.uint8, device=dev))
+            obs, rewards, dones = out
+            ob = nv.Obs(**{k: obs[k].data_ptr() for k in OBS_KEYS}) if with_obs else None
+        else:
+            obs, rewards, dones = (self.obs if with_obs else None), self.rewards, self.dones
+            ob = self._ob if with_obs else None
+        with self._on_device:
+            rc = self.lib.wh_multi_step(C.byref(self._cfg), C.byref(self._st), N, self.env_id0, self.seed, T,
+                                        _ptr(actions), int(solver_seed), thr, rewards.data_ptr(), dones.data_ptr(),
+                                        self.stats.data_ptr(), C.byref(ob) if ob is not None else None, flags,
+                                        self._stream())
+        nv.check(rc, "wh_multi_step")
+        self.launches += 1
+        return obs, rewards, dones
+
     def build_obs(self, flavour=nv.OBS_STEP):
         with self._on_device:
             rc = self.lib.wh_build_obs(C.byref(self._cfg), C.byref(self._st), self.N, int(flavour),

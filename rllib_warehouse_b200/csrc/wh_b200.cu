@@ -47,7 +47,7 @@ struct Tile {
     env_t e, env0;   // this lane's environment; the first environment of the warp
     bool live;
     __device__ __forceinline__ Tile(const KParams &P, const Group<GC> &g) {
-        const uint32_t warp = blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5);
+        const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // blockDim.x <= BLOCK
         env0 = warp * (uint32_t)g.epw;
         const uint32_t env = env0 + (uint32_t)g.gi, n = (uint32_t)P.N;
         live = !g.ghost && env < n;
@@ -150,11 +150,12 @@ __global__ void __launch_bounds__(BLOCK, (RC == 16 ? WH_MIN_BLOCKS_LARGE : RC ==
         meta = true;
     }
     if (t.live) store_env(P, g, e, R, (RC ? 4 * GC : P.P), s, meta);
-    if (FLAT)   // RLlib-flattened float32 layout instead of the dict keys (separate instantiation)
+    if constexpr (FLAT)   // RLlib-flattened float32 layout instead of the dict keys (separate instantiation)
         build_obs_flat<GC, RC>(P, g, e, R, s, active, tpos16, flavour, t.live, P.flat_out,
-                               reinterpret_cast<float *>(StageMem<GC, RC, true>::mine(smem, g)));
+                               reinterpret_cast<float *>(StageMem<GC, RC, true>::mine(smem, g)),
+                               reinterpret_cast<float *>(StageMem<GC, RC, true>::warp_area(smem)), t.env0);
     else if (P.obs.requests)
-        build_obs<GC, RC>(P, g, e, R, s, active, tpos16, flavour, t.live, StageMem<GC, RC>::mine(smem, g),
+        build_obs<GC, RC>(P, P.obs, g, e, R, s, active, tpos16, flavour, t.live, StageMem<GC, RC>::mine(smem, g),
                           StageMem<GC, RC>::warp_area(smem), t.env0);
 }
 
@@ -191,6 +192,77 @@ __global__ void __launch_bounds__(BLOCK, (RC == 16 ? 4 : WH_MIN_BLOCKS)) k_rollo
     }
 }
 
+// `n_steps` consecutive env.step calls in ONE launch (wh_multi_step): the state stays in registers between
+// the steps, every step's rewards / dones / observations are written exactly as n_steps single launches
+// would write them — either into per-step slices of [T,N,...] tensors (WH_FLAG_PER_STEP_OUT) or over the
+// resident [N,...] tensors. Actions: open-loop int32 [T,N,R], or the in-kernel greedy solver. Envs are
+// warp-private, so the steps of different warps drift apart freely: no per-step launch ramp / tail, which
+// is what bounds launch-sized batches (BASELINE configs[1]: 4 096 Small envs, configs[2]: 65 536 Medium).
+template <int GC, int RC, bool GREEDY>
+__global__ void __launch_bounds__(BLOCK, (RC == 16 ? WH_MIN_BLOCKS_LARGE : RC == 9 ? WH_MIN_BLOCKS_MEDIUM : RC == 4 ? WH_MIN_BLOCKS_SMALL : WH_MIN_BLOCKS)) k_multi(const __grid_constant__ KParams P) {
+    __shared__ __align__(16) unsigned char smem[StageMem<GC, RC>::BYTES];
+    const Group<GC> g(P.G);
+    const Tile<GC> t(P, g);
+    const int R = RC ? RC : P.R;
+    const env_t e = t.e;
+    const uint32_t env_id = (uint32_t)P.env_id0 + e;
+    EnvRegs s;
+    load_env(P, g, e, R, (RC ? 4 * GC : P.P), s);
+    const bool auto_reset = (P.flags & WH_FLAG_AUTO_RESET) != 0;
+    const bool per_step = (P.flags & WH_FLAG_PER_STEP_OUT) != 0;
+    wh_obs o = P.obs;
+    const bool with_obs = o.requests != nullptr;
+    const int32_t *acts = P.actions;
+    float *rew = P.rewards;
+    uint8_t *dn = P.dones;
+    const size_t NR = (size_t)P.N * R, N = (size_t)P.N;
+    float ret = 0.0f;
+    bool done = false;
+    for (int it = 0; it < P.n_steps; ++it) {
+        int act = -1;
+        if (GREEDY) act = greedy_from_state<GC, RC>(P, g, R, env_id, s);
+        else if (g.gl < R) act = acts[e * R + g.gl];
+        s.time += 1;                                                           // core.py:267
+        do_moves<GC, RC>(P, g, R, s.A, act, -1, false, s.pos16);
+        const StepOut so = do_world(P, g, e, R, env_id, s, false);
+        done = s.time >= P.episode;                                            // core.py:438
+        if (per_step) {
+            if (t.live && g.gl < R) rew[e * R + g.gl] = so.reward;              // core.py:435
+            if (t.live && g.gl == 0) dn[e] = done ? 1 : 0;
+        } else {
+            ret += so.reward;
+        }
+        account_episode(P, g.gl == 0 && t.live, e, so, s, done, auto_reset);
+        unsigned long long active = so.active;
+        int flavour = WH_OBS_STEP;
+        if (auto_reset && __any_sync(FULL, done)) {
+            const unsigned long long a2 = do_reset(P, g, e, R, env_id, s, false, done && t.live);
+            if (done) { active = a2; flavour = WH_OBS_RESET; }
+        }
+        if (with_obs) {
+            build_obs<GC, RC>(P, o, g, e, R, s, active, so.tpos16, flavour, t.live, StageMem<GC, RC>::mine(smem, g),
+                              StageMem<GC, RC>::warp_area(smem), t.env0);
+            __syncwarp();                                                      // staging is reused by the next step
+        }
+        if (!GREEDY) acts += NR;
+        if (per_step) {
+            rew += NR; dn += N;
+            if (with_obs) {
+                o.num_agents += NR; o.self_position += 2 * NR; o.self_availability += NR; o.self_delivery_target += 2 * NR;
+                o.other_positions += 2 * NR * (R - 1); o.other_availabilities += NR * (R - 1);
+                o.other_delivery_targets += 2 * NR * (R - 1); o.requests += 4 * NR * R;
+            }
+        }
+    }
+    if (t.live) {
+        store_env(P, g, e, R, (RC ? 4 * GC : P.P), s, true);
+        if (!per_step) {
+            if (g.gl < R) P.rewards[e * R + g.gl] = ret;
+            if (g.gl == 0) P.dones[e] = done ? 1 : 0;
+        }
+    }
+}
+
 // Warehouse.reset — core.py:167-260
 template <int GC, int RC>
 __global__ void __launch_bounds__(BLOCK) k_reset(const __grid_constant__ KParams P) {
@@ -209,7 +281,7 @@ __global__ void __launch_bounds__(BLOCK) k_reset(const __grid_constant__ KParams
         if (g.gl == 0) reinterpret_cast<int4 *>(P.acc)[e] = make_int4(0, 0, 0, 0);
     }
     if (P.obs.requests)
-        build_obs<GC, RC>(P, g, e, R, s, active, 0u, WH_OBS_RESET, doit, StageMem<GC, RC>::mine(smem, g),
+        build_obs<GC, RC>(P, P.obs, g, e, R, s, active, 0u, WH_OBS_RESET, doit, StageMem<GC, RC>::mine(smem, g),
                           StageMem<GC, RC>::warp_area(smem), t.env0);
 }
 
@@ -223,7 +295,7 @@ __global__ void __launch_bounds__(BLOCK) k_obs(const __grid_constant__ KParams P
     EnvRegs s;
     load_env(P, g, t.e, R, (RC ? 4 * GC : P.P), s);
     const unsigned long long active = active_mask(g, s.pt4);
-    build_obs<GC, RC>(P, g, t.e, R, s, active, target_cell16<GC>(P, s.atgt), P.flavour, t.live, StageMem<GC, RC>::mine(smem, g),
+    build_obs<GC, RC>(P, P.obs, g, t.e, R, s, active, target_cell16<GC>(P, s.atgt), P.flavour, t.live, StageMem<GC, RC>::mine(smem, g),
                       StageMem<GC, RC>::warp_area(smem), t.env0);
 }
 
@@ -238,7 +310,8 @@ __global__ void __launch_bounds__(BLOCK) k_obs_flat(const __grid_constant__ KPar
     load_env(P, g, t.e, R, (RC ? 4 * GC : P.P), s);
     const unsigned long long active = active_mask(g, s.pt4);
     build_obs_flat<GC, RC>(P, g, t.e, R, s, active, target_cell16<GC>(P, s.atgt), P.flavour, t.live,
-                           P.flat_out, reinterpret_cast<float *>(StageMem<GC, RC, true>::mine(smem, g)));
+                           P.flat_out, reinterpret_cast<float *>(StageMem<GC, RC, true>::mine(smem, g)),
+                           reinterpret_cast<float *>(StageMem<GC, RC, true>::warp_area(smem)), t.env0);
 }
 
 // WarehouseRandomGreedySolver.compute_action on observation tensors — solvers.py:27-58.
@@ -373,7 +446,7 @@ static bool obs_ok(const wh_obs *o) {
            o->other_positions && o->other_availabilities && o->other_delivery_targets && o->requests;
 }
 
-enum Kind { K_STEP, K_GSTEP, K_STEP_FLAT, K_RESET, K_OBS, K_OBS_FLAT, K_GREEDY, K_ROLLOUT };
+enum Kind { K_STEP, K_GSTEP, K_STEP_FLAT, K_RESET, K_OBS, K_OBS_FLAT, K_GREEDY, K_ROLLOUT, K_MULTI, K_GMULTI };
 
 // Step kernels are launched back to back, one per env.step, each depending on the one before
 // through the state tensors. Programmatic stream serialization lets the driver schedule step
@@ -431,6 +504,25 @@ static void launch_kind(Kind kind, const KParams &K, cudaStream_t s) {
     case K_OBS: k_obs<GC, RC><<<grid, BLOCK, 0, s>>>(K); break;
     case K_OBS_FLAT: k_obs_flat<GC, RC><<<grid, BLOCK, 0, s>>>(K); break;
     case K_ROLLOUT: k_rollout<GC, RC><<<grid, BLOCK, 0, s>>>(K); break;
+    case K_MULTI:
+    case K_GMULTI: {
+        // launch-sized batches: with fewer warps than the GPU has schedulers, spread them over the SMs
+        // (2-warp blocks) instead of packing 8 per block
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+        const unsigned threads = warps >= (long long)sms * 16 ? BLOCK : 64;
+        const unsigned mgrid = (unsigned)((warps * 32 + threads - 1) / threads);
+        if (dyn) {
+            static std::atomic<bool> once[2];
+            if (!once[kind == K_GMULTI].exchange(true)) {
+                cudaFuncSetAttribute(k_multi<GC, RC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+                cudaFuncSetAttribute(k_multi<GC, RC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+            }
+        }
+        if (kind == K_GMULTI) k_multi<GC, RC, true><<<mgrid, threads, dyn, s>>>(K);
+        else k_multi<GC, RC, false><<<mgrid, threads, dyn, s>>>(K);
+        break;
+    }
     default: break;
     }
 }
@@ -591,6 +683,23 @@ int wh_greedy_rollout(const wh_config *cfg, const wh_state *st, int64_t n_envs, 
     K.rand_thr = rand_threshold; K.n_steps = n_steps;
     K.rewards = reward_sums; K.dones = dones; K.stats = stats; K.flags = flags;
     return launch(K_ROLLOUT, K, sh, stream);
+}
+
+int wh_multi_step(const wh_config *cfg, const wh_state *st, int64_t n_envs, int64_t env_id0, uint64_t seed,
+                  int n_steps, const int32_t *actions, uint64_t solver_seed, uint64_t rand_threshold,
+                  float *rewards, uint8_t *dones, unsigned long long *stats, const wh_obs *obs, int flags,
+                  void *stream) {
+    KParams K; Shape sh;
+    if (int rc = fill_params(cfg, K, sh)) return rc;
+    if (n_envs == 0 || n_steps == 0) return 0;
+    if (!state_ok(st) || !rewards || !dones || n_steps < 0 || (obs && !obs_ok(obs))) return WH_E_ARG;
+    if (flags & ~(WH_FLAG_AUTO_RESET | WH_FLAG_PER_STEP_OUT)) return WH_E_ARG;
+    set_state(K, st);
+    if (obs) K.obs = *obs;
+    K.N = n_envs; K.env_id0 = env_id0; K.seed = seed; K.solver_seed = solver_seed;
+    K.rand_thr = rand_threshold; K.n_steps = n_steps; K.actions = actions;
+    K.rewards = rewards; K.dones = dones; K.stats = stats; K.flags = flags;
+    return launch(actions ? K_MULTI : K_GMULTI, K, sh, stream);
 }
 
 int wh_build_obs(const wh_config *cfg, const wh_state *st, int64_t n_envs, int flavour,

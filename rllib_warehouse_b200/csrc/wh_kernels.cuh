@@ -568,10 +568,11 @@ struct ObsStage {
 };
 
 template <int GC, int RC>
-__device__ __forceinline__ void build_obs(const KParams &P, const Group<GC> &g, env_t e, int R,
+__device__ __forceinline__ void build_obs(const KParams &P, const wh_obs &o, const Group<GC> &g, env_t e, int R,
                                           const EnvRegs &s, unsigned long long active, uint32_t tpos16,
                                           int flavour, bool live, unsigned char *stage,
                                           unsigned char *wstage = nullptr, env_t env0 = 0) {
+    // o: where the observation goes (P.obs, or a per-step slice of [T,N,...] tensors in k_multi);
     // stage: this environment's staging slot; wstage / env0: the warp's whole staging area and its
     // first environment (used by the warp-cooperative copy-out only)
     const Geo<GC> geo(P);
@@ -603,7 +604,6 @@ __device__ __forceinline__ void build_obs(const KParams &P, const Group<GC> &g, 
         rq = make_int4(pc & 0xFF, pc >> 8, dc & 0xFF, dc >> 8);
     }
 
-    const wh_obs &o = P.obs;
     const uint32_t row0 = e * (uint32_t)R;
     if (live && g.gl < R) {
         o.num_agents[row0 + g.gl] = s.A;
@@ -792,19 +792,61 @@ __device__ __forceinline__ void build_obs(const KParams &P, const Group<GC> &g, 
 // other_delivery_targets(2(R-1)) other_positions(2(R-1)) requests(4R) self_availability(1)
 // self_delivery_target(2) self_position(2). Same values as build_obs (core.py:371-432 / 224-260).
 // ---------------------------------------------------------------------------------------------
+// Every float of an environment's [R, 9R+1] block is a copy of one entry of a small per-env VALUE TABLE
+//   V = [ num_agents | availability[R] | delivery-target cell[R][2] | position[R][2] | requests[R][4] ]
+// (9R+1 entries, the padded tables of core.py:372-418), and WHICH entry is a static function of the
+// position in the block (row a, column f): the "table without row a" of core.py:424-427 is a +1 index
+// shift behind the deleted row, core.py:428 always deletes row 1. In the reset flavour every delivery
+// target is the null cell and every availability 0 (core.py:233-236), so the same map serves both.
+// FlatMap<RC> is that map, built at compile time; entries are SWIZZLED table addresses (see swz).
+template <int RC>
+struct FlatMap {
+    static constexpr int R = RC ? RC : 1;
+    static constexpr int F = 9 * R + 1;                 // floats per agent row
+    static constexpr int RF = R * F;                    // floats per environment (always even)
+    static constexpr int S4 = (F + 3) / 4;              // table words per swizzle plane
+    static constexpr int VS = 4 * S4;                   // table words per environment
+    // Table entry s lives at word (s >> 2) + (s & 3) * S4: a lane that copies 4 consecutive floats reads
+    // entries c + 4*lane + j (j = 0..3), i.e. for fixed j CONSECUTIVE words across the warp — no bank
+    // conflicts inside a segment.
+    __host__ __device__ static constexpr int swz(int s) { return (s >> 2) + (s & 3) * S4; }
+    __host__ __device__ static constexpr int src(int a, int f) {
+        if (f == 0) return 0;                                                              // num_agents
+        if (f < R) { const int j = f - 1; return 1 + j + (j >= a ? 1 : 0); }               // other_availabilities
+        if (f < 3 * R - 2) { const int j2 = f - R, j = j2 >> 1; return 1 + R + 2 * (j + (j >= 1 ? 1 : 0)) + (j2 & 1); }  // core.py:428
+        if (f < 5 * R - 4) { const int j2 = f - (3 * R - 2), j = j2 >> 1; return 1 + 3 * R + 2 * (j + (j >= a ? 1 : 0)) + (j2 & 1); }
+        if (f < 9 * R - 4) return 1 + 5 * R + (f - (5 * R - 4));                            // requests
+        if (f == 9 * R - 4) return 1 + a;                                                  // self_availability
+        if (f < 9 * R - 1) return 1 + R + 2 * a + (f - (9 * R - 3));                        // self_delivery_target
+        return 1 + 3 * R + 2 * a + (f - (9 * R - 1));                                      // self_position
+    }
+    alignas(16) uint8_t m[RF + 8];
+    constexpr FlatMap() : m{} {
+        for (int a = 0; a < R; ++a)
+            for (int f = 0; f < F; ++f) m[a * F + f] = (uint8_t)swz(src(a, f));
+    }
+};
+__device__ const FlatMap<4> d_flat_map4{};
+__device__ const FlatMap<9> d_flat_map9{};
+__device__ const FlatMap<16> d_flat_map16{};
+template <int RC>
+__device__ __forceinline__ const uint8_t *flat_map() {
+    if constexpr (RC == 4) return d_flat_map4.m;
+    else if constexpr (RC == 9) return d_flat_map9.m;
+    else return d_flat_map16.m;
+}
+
 template <int RC>
 struct FlatStage {
-    static constexpr int F = 9 * RC + 1;                                     // floats per agent row
-    static constexpr int VEC = RC == 0 ? 1 : ((RC * F) % 4 == 0 ? 4 : ((RC * F) % 2 == 0 ? 2 : 1));
-    // rows per staged chunk: chunk floats must be a multiple of VEC
-    static constexpr int CHUNK = RC == 0 ? 1 : ((F % VEC == 0) ? (RC < 4 ? RC : 4) : ((2 * F) % VEC == 0 ? 2 : 4));
-    static constexpr int BYTES = RC ? ((CHUNK * F * 4 + 15) / 16) * 16 : 16;
+    static constexpr int BYTES = RC ? FlatMap<RC>::VS * 4 : 16;            // one environment's value table
 };
 
 template <int GC, int RC>
 __device__ __forceinline__ void build_obs_flat(const KParams &P, const Group<GC> &g, env_t e, int R,
                                                const EnvRegs &s, unsigned long long active, uint32_t tpos16,
-                                               int flavour, bool live, float *out, float *stage) {
+                                               int flavour, bool live, float *out, float *stage,
+                                               float *wstage = nullptr, env_t env0 = 0) {
+    // stage: this environment's value table; wstage / env0: the warp's tables and its first environment
     const Geo<GC> geo(P);
     const int null_pos = geo.null_pos;
     const uint32_t null16 = geo.null16();
@@ -813,9 +855,6 @@ __device__ __forceinline__ void build_obs_flat(const KParams &P, const Group<GC>
     const uint32_t ppos = real ? s.pos16 : null16;
     const uint32_t avail = (flavour == WH_OBS_STEP && real && !delivering) ? 1u : 0u;
     const uint32_t tpos = (flavour == WH_OBS_STEP && delivering) ? tpos16 : null16;
-    const uint32_t mine = (ppos & 0x7Fu) | (((ppos >> 8) & 0x7Fu) << 7) | ((tpos & 0x7Fu) << 14) |
-                          (((tpos >> 8) & 0x7Fu) << 21) | (avail << 28);
-    const uint32_t next = g.shfl_down1(mine);
     const bool have = g.gl < R && g.gl < __popcll(active);
     const int p = ((RC != 0 && RC <= 4) ? nth_set_small<(RC ? RC : 1)>((uint32_t)active, have ? g.gl : 0)
                                         : nth_set64<Group<GC>::PBITS>(active, have ? g.gl : 0)) & 63;
@@ -826,59 +865,95 @@ __device__ __forceinline__ void build_obs_flat(const KParams &P, const Group<GC>
         const uint32_t dc = delivery_cell16((int)((w4 >> (8 * (p & 3))) & 0x3Fu), geo.dim);
         rq = make_float4((float)(pc & 0xFF), (float)(pc >> 8), (float)(dc & 0xFF), (float)(dc >> 8));
     }
-    const int F = 9 * R + 1;
     const float n_agents = (float)s.A;
-    const bool writer = !g.ghost;
-    auto px = [](uint32_t v) { return (float)(v & 0x7F); };
-    auto py = [](uint32_t v) { return (float)((v >> 7) & 0x7F); };
-    auto tx = [](uint32_t v) { return (float)((v >> 14) & 0x7F); };
-    auto ty = [](uint32_t v) { return (float)((v >> 21) & 0x7F); };
-    auto av = [](uint32_t v) { return (float)((v >> 28) & 1); };
-    const uint32_t t_row1 = (g.gl >= 1) ? next : mine;       // core.py:428 (step) drops row 1
-    // writes agent row `a` of this env at dst[0 .. F)
-    auto emit_row = [&](float *dst, int a) {
-        if (g.gl == 0) dst[0] = n_agents;
-        if (g.gl < R - 1) {
-            const uint32_t o = (g.gl >= a) ? next : mine;                       // core.py:426-427
-            const uint32_t t = (flavour == WH_OBS_STEP) ? t_row1 : o;
-            dst[1 + g.gl] = av(o);
-            dst[R + 2 * g.gl] = tx(t); dst[R + 2 * g.gl + 1] = ty(t);
-            dst[3 * R - 2 + 2 * g.gl] = px(o); dst[3 * R - 2 + 2 * g.gl + 1] = py(o);
-        }
-        if (g.gl < R) {
-            float *q = dst + 5 * R - 4 + 4 * g.gl;
-            q[0] = rq.x; q[1] = rq.y; q[2] = rq.z; q[3] = rq.w;
-        }
-        if (g.gl == a) {
-            dst[9 * R - 4] = av(mine);
-            dst[9 * R - 3] = tx(mine); dst[9 * R - 2] = ty(mine);
-            dst[9 * R - 1] = px(mine); dst[9 * R] = py(mine);
-        }
-    };
-    float *env_out = out + (long long)e * R * F;
     if constexpr (RC != 0) {
-        using St = FlatStage<RC>;
+        using M = FlatMap<RC>;
+        constexpr int EPW = 32 / GC;
+        // ---- the environment's value table (each lane contributes the entries of its own row) ----
+        if (!g.ghost && g.gl < RC) {
+            if (g.gl == 0) stage[M::swz(0)] = n_agents;
+            const int sa = 1 + g.gl, st_ = 1 + RC + 2 * g.gl, sp = 1 + 3 * RC + 2 * g.gl, sr = 1 + 5 * RC + 4 * g.gl;
+            auto at = [&](int i) -> float & { return stage[(i >> 2) + (i & 3) * M::S4]; };
+            at(sa) = (float)avail;
+            at(st_) = (float)(tpos & 0xFF); at(st_ + 1) = (float)(tpos >> 8);
+            at(sp) = (float)(ppos & 0xFF); at(sp + 1) = (float)(ppos >> 8);
+            at(sr) = rq.x; at(sr + 1) = rq.y; at(sr + 2) = rq.z; at(sr + 3) = rq.w;
+        }
+        __syncwarp();
+        // ---- copy-out: the warp's EPW environments are ONE contiguous range of the output; all 32 lanes
+        // stream it with 128-bit stores, every float fetched through the static map ----
+        const uint8_t *map = flat_map<RC>();
+        const uint32_t n = (uint32_t)P.N;
+        const int n_live = (env0 + EPW <= n) ? EPW : (int)(n - env0);        // k_step / k_obs_flat: a prefix
+        const int limit = (env0 < n) ? n_live * M::RF : 0;                   // floats of this warp
+        float *wout = out + (size_t)env0 * M::RF;
+        const int head = (M::RF % 4 == 0) ? 0 : (int)((0u - env0 * (uint32_t)M::RF) & 3u);   // floats before the first 16-byte boundary (0 or 2)
+        auto fetch2 = [&](int k) -> float2 {             // floats k, k+1 of the warp's range (k even: never straddles an env)
+            int env = 0, kk = k;
+            if constexpr (EPW <= 3) {
 #pragma unroll
-        for (int a0 = 0; a0 < RC; a0 += St::CHUNK) {
-            const int rows = (RC - a0 < St::CHUNK) ? RC - a0 : St::CHUNK;
-#pragma unroll
-            for (int la = 0; la < St::CHUNK; ++la)
-                if (la < rows && writer) emit_row(stage + la * St::F, a0 + la);
-            __syncwarp();
-            if (live) {
-                const int nvec = rows * St::F / St::VEC;
-                float *dst = env_out + a0 * St::F;
-                for (int i = g.gl; i < nvec; i += GC) {
-                    if (St::VEC == 4) WH_ST(reinterpret_cast<float4 *>(dst) + i, reinterpret_cast<const float4 *>(stage)[i]);
-                    else if (St::VEC == 2) WH_ST(reinterpret_cast<float2 *>(dst) + i, reinterpret_cast<const float2 *>(stage)[i]);
-                    else WH_ST(dst + i, stage[i]);
+                for (int t = 1; t < EPW; ++t) if (k >= t * M::RF) { env = t; kk = k - t * M::RF; }
+            } else {
+                env = (int)(((uint32_t)k * (uint32_t)((65536 + M::RF - 1) / M::RF)) >> 16);   // k / RF for k < EPW*RF (checked below)
+                kk = k - env * M::RF;
+            }
+            const uint32_t mm = *reinterpret_cast<const uint16_t *>(map + kk);
+            const float *v = wstage + env * M::VS;
+            return make_float2(v[mm & 0xFFu], v[mm >> 8]);
+        };
+        static_assert(M::RF % 2 == 0, "pairs never straddle environments");
+        static_assert(EPW <= 3 || ((EPW * M::RF - 1) * ((65536 + M::RF - 1) / M::RF)) >> 16 == EPW - 1, "reciprocal division range");
+        const int nb = limit > head ? (limit - head) >> 2 : 0;               // whole float4 in the range (none for a warp past N)
+        constexpr int ITERS = (EPW * M::RF / 4 + 31) / 32;
+#pragma unroll 4
+        for (int it = 0; it < ITERS; ++it) {
+            const int i = g.lane + 32 * it;
+            if (i < nb) {
+                const int k = head + 4 * i;
+                const float2 a = fetch2(k), b = fetch2(k + 2);
+                WH_ST(reinterpret_cast<float4 *>(wout + k), make_float4(a.x, a.y, b.x, b.y));
+            }
+        }
+        if (M::RF % 4 != 0) {                                                // 8-byte head / tail of a misaligned range
+            if (g.lane == 0 && head == 2 && limit >= 2) WH_ST(reinterpret_cast<float2 *>(wout), fetch2(0));
+            const int tail = head + 4 * nb;
+            if (g.lane == 1 && limit > 0 && tail < limit) WH_ST(reinterpret_cast<float2 *>(wout + tail), fetch2(tail));
+        }
+        (void)live;
+    } else {
+        // runtime-R geometries: every lane writes its pieces of each agent row straight to global memory
+        const uint32_t mine = (ppos & 0x7Fu) | (((ppos >> 8) & 0x7Fu) << 7) | ((tpos & 0x7Fu) << 14) |
+                              (((tpos >> 8) & 0x7Fu) << 21) | (avail << 28);
+        const uint32_t next = g.shfl_down1(mine);
+        const int F = 9 * R + 1;
+        auto px = [](uint32_t v) { return (float)(v & 0x7F); };
+        auto py = [](uint32_t v) { return (float)((v >> 7) & 0x7F); };
+        auto tx = [](uint32_t v) { return (float)((v >> 14) & 0x7F); };
+        auto ty = [](uint32_t v) { return (float)((v >> 21) & 0x7F); };
+        auto av = [](uint32_t v) { return (float)((v >> 28) & 1); };
+        const uint32_t t_row1 = (g.gl >= 1) ? next : mine;       // core.py:428 (step) drops row 1
+        float *env_out = out + (long long)e * R * F;
+        if (live)
+            for (int a = 0; a < R; ++a) {
+                float *dst = env_out + a * F;
+                if (g.gl == 0) dst[0] = n_agents;
+                if (g.gl < R - 1) {
+                    const uint32_t o = (g.gl >= a) ? next : mine;                   // core.py:426-427
+                    const uint32_t t = (flavour == WH_OBS_STEP) ? t_row1 : o;
+                    dst[1 + g.gl] = av(o);
+                    dst[R + 2 * g.gl] = tx(t); dst[R + 2 * g.gl + 1] = ty(t);
+                    dst[3 * R - 2 + 2 * g.gl] = px(o); dst[3 * R - 2 + 2 * g.gl + 1] = py(o);
+                }
+                if (g.gl < R) {
+                    float *q = dst + 5 * R - 4 + 4 * g.gl;
+                    q[0] = rq.x; q[1] = rq.y; q[2] = rq.z; q[3] = rq.w;
+                }
+                if (g.gl == a) {
+                    dst[9 * R - 4] = av(mine);
+                    dst[9 * R - 3] = tx(mine); dst[9 * R - 2] = ty(mine);
+                    dst[9 * R - 1] = px(mine); dst[9 * R] = py(mine);
                 }
             }
-            __syncwarp();
-        }
-    } else {
-        if (live)
-            for (int a = 0; a < R; ++a) emit_row(env_out + a * F, a);
     }
 }
 

@@ -186,29 +186,54 @@ def test_philox_matches_oracle():
         same_state(g, c, f"seed {seed}")
 
 
+def oracle_flat(cpu):
+    """The ORACLE's dict observations in RLlib's Dict-flattening order (alphabetical keys, core.py:119-148),
+    float32 [N, R, 9R+1] — the comparand of every flat-observation test (numpy only, no CUDA involved)."""
+    n, R = cpu.N, cpu.R
+    return np.concatenate([cpu.obs[k].reshape(n, R, -1).astype(np.float32) for k in sorted(cpu.obs)], axis=2)
+
+
+def oracle_auto_reset(cpu, done):
+    """What WH_FLAG_AUTO_RESET does in-kernel, on the oracle: finished envs are reset and show their
+    reset-flavour observation, everything else keeps the step-flavour one."""
+    cpu.build_obs(0)
+    if done.any():
+        step_obs = {k: v.copy() for k, v in cpu.obs.items()}
+        cpu.reset(env_mask=done.astype(np.uint8))          # rebuilds every env's obs in reset flavour
+        cpu.state["acc"][done] = 0
+        for k in cpu.obs:
+            cpu.obs[k][~done] = step_obs[k][~done]
+
+
 @pytest.mark.parametrize("size", list(SIZES))
 def test_flat_observations(size):
-    """RLlib-flattened float32 observations == the (oracle-verified) dict observations flattened in
-    alphabetical key order, for both flavours and per-env agent counts."""
-    from rllib_warehouse_b200 import VARIANTS, BatchedWarehouse
+    """RLlib-flattened float32 observations (wh_build_obs_flat) == the ORACLE's dict observations
+    flattened in alphabetical key order, for both flavours, per-env agent counts, batch sizes that leave
+    partial warps, and the runtime-R path."""
     from rllib_warehouse_b200 import _native as nv
-    n = 1000
-    env = BatchedWarehouse(VARIANTS[size].replace(random_num_agents=True), n, seed=4)
-    obs = env.reset()
-    flat = env.build_obs_flat(nv.OBS_RESET)
-    assert flat.shape == (n, env.R, 9 * env.R + 1) and flat.dtype == torch.float32
-    assert torch.equal(flat, env.flatten_obs(obs))
-    for t in range(30):
-        obs, _, _ = env.greedy_step()
-        if t % 5 == 0:
-            assert torch.equal(env.build_obs_flat(), env.flatten_obs(obs)), t
-    cfgs = [(6, 14, (3, 7, 11)), (3, 11, (5,))]
-    from rllib_warehouse_b200 import WarehouseConfig
-    for R, dim, racks in cfgs:           # runtime-R path
-        env = BatchedWarehouse(WarehouseConfig(R, dim, racks, 40, 25, R), 77, seed=1)
-        env.reset()
-        obs, _, _ = env.greedy_step()
-        assert torch.equal(env.build_obs_flat(), env.flatten_obs(obs))
+    for n in (1000, 37, 1):
+        gpu, cpu = pair(size, n, seed=4, train=True)
+        gpu.reset(); cpu.reset()
+        flat = gpu.build_obs_flat(nv.OBS_RESET)
+        assert flat.shape == (n, gpu.R, 9 * gpu.R + 1) and flat.dtype == torch.float32
+        assert np.array_equal(flat.cpu().numpy(), oracle_flat(cpu)), "reset flavour"
+        for t in range(30 if n == 1000 else 6):
+            gpu.greedy_step(with_obs=False)
+            cpu.greedy(); cpu.step(cpu.actions)
+            if t % 5 == 0:
+                assert np.array_equal(gpu.build_obs_flat().cpu().numpy(), oracle_flat(cpu)), (n, t)
+                # the oracle also agrees with a plain flatten of the CUDA dict observations
+                gpu.build_obs()
+                assert np.array_equal(gpu.flatten_obs(gpu.obs).cpu().numpy(), oracle_flat(cpu)), (n, t)
+    from rllib_warehouse_b200 import BatchedWarehouse, WarehouseConfig
+    for R, dim, racks in [(6, 14, (3, 7, 11)), (3, 11, (5,))]:           # runtime-R path
+        gpu = BatchedWarehouse(WarehouseConfig(R, dim, racks, 40, 25, R), 77, seed=1)
+        cpu = wo.OracleEnv(wo.make_config(R, dim, list(racks), 40, 25, R), 77, seed=1)
+        gpu.reset(); cpu.reset()
+        assert np.array_equal(gpu.build_obs_flat(nv.OBS_RESET).cpu().numpy(), oracle_flat(cpu))
+        gpu.greedy_step(with_obs=False)
+        cpu.greedy(); cpu.step(cpu.actions)
+        assert np.array_equal(gpu.build_obs_flat().cpu().numpy(), oracle_flat(cpu))
 
 
 @pytest.mark.parametrize("compact", [False, True])
@@ -256,25 +281,29 @@ def test_host_buffer_layer(compact):
 
 @pytest.mark.parametrize("size", list(SIZES))
 def test_step_with_fused_flat_observations(size):
-    """wh_step_flat (step kernel emitting RLlib-flattened float32 obs itself) == wh_step + flatten,
-    across an auto-reset boundary (reset-flavour observations for finished envs)."""
+    """wh_step_flat (the step kernel emitting RLlib-flattened float32 observations itself) against the
+    ORACLE (step + dict observations flattened alphabetically), with per-env agent counts, random dict
+    orders and absent agents, across auto-reset boundaries (finished envs show their reset-flavour
+    observation), at batch sizes with partial warps."""
     from rllib_warehouse_b200 import VARIANTS, BatchedWarehouse
-    n = 777
-    cfg = VARIANTS[size].replace(random_num_agents=True, episode_duration=12)
-    a = BatchedWarehouse(cfg, n, seed=9, auto_reset=True)
-    b = BatchedWarehouse(cfg, n, seed=9, auto_reset=True)
-    a.reset(); b.reset()
-    rng = np.random.Generator(np.random.PCG64(2))
-    for t in range(30):
-        acts = rng.integers(-1, 9, size=(n, a.R)).astype(np.int32)
-        order = np.stack([rng.permutation(a.R) for _ in range(n)]).astype(np.int32) if t % 4 == 0 else None
-        obs, rew, dones = a.step(acts, order=order)
-        flat, rew2, dones2 = b.step_flat(acts, order=order)
-        assert torch.equal(flat, a.flatten_obs(obs)), t
-        assert torch.equal(rew, rew2) and torch.equal(dones, dones2)
-    for k in a.state:
-        assert torch.equal(a.state[k], b.state[k]), k
-    assert torch.equal(a.stats, b.stats) and int(a.stats[0]) == 2 * n
+    for n in (777, 5):
+        cfg = VARIANTS[size].replace(random_num_agents=True, episode_duration=12)
+        b = BatchedWarehouse(cfg, n, seed=9, auto_reset=True)
+        kw = dict(wo.VARIANTS[size]); kw["episode"] = 12
+        cpu = wo.OracleEnv(wo.make_config(random_num_agents=True, **kw), n, seed=9)
+        b.reset(); cpu.reset()
+        rng = np.random.Generator(np.random.PCG64(2))
+        for t in range(30):
+            acts = rng.integers(-1, 9, size=(n, b.R)).astype(np.int32)
+            order = np.stack([rng.permutation(b.R) for _ in range(n)]).astype(np.int32) if t % 4 == 0 else None
+            flat, rew, dones = b.step_flat(acts, order=order)
+            cpu.step(acts, order=order, with_obs=False)
+            assert np.array_equal(rew.cpu().numpy(), cpu.rewards), t
+            assert np.array_equal(dones.cpu().numpy(), cpu.dones), t
+            oracle_auto_reset(cpu, cpu.dones.astype(bool))
+            assert np.array_equal(flat.cpu().numpy(), oracle_flat(cpu)), (n, t)
+            same_state(b, cpu, f"step {t}")
+        assert np.array_equal(b.stats.cpu().numpy(), cpu.stats) and int(cpu.stats[0]) == 2 * n
 
 
 def test_cuda_graph_replay_matches_eager():
@@ -553,3 +582,52 @@ def test_multi_step_greedy_rollout_kernel(size, n, p):
                 cpu.reset(env_mask=done.astype(np.uint8))
         same_state(one, cpu, "rollout kernel vs oracle")
         assert np.array_equal(one.stats.cpu().numpy(), cpu.stats)
+
+
+@pytest.mark.parametrize("size,n,T", [("small", 4097, 205), ("medium", 1000, 60), ("large", 515, 40)])
+def test_multi_step_open_loop_actions_every_step_vs_oracle(size, n, T):
+    """wh_multi_step with an open-loop [T,N,R] action tensor and per-step outputs: ONE launch runs the whole
+    BASELINE configs[1] episode (Small, 4 096(+1) envs, random actions incl. absent agents, T = 205 passes
+    the step-200 mass expiry); every step's observations, rewards and dones — and the final state — are
+    bit-identical to the oracle stepped T times."""
+    gpu, cpu = pair(size, n, seed=0xBEEF)
+    gpu.reset(); cpu.reset()
+    rng = np.random.Generator(np.random.PCG64(17))
+    actions = rng.integers(-1, 9, size=(T, n, cpu.R)).astype(np.int32)
+    obs, rew, dones = gpu.multi_step(T, actions=actions, per_step=True)
+    obs = {k: v.cpu().numpy() for k, v in obs.items()}
+    rew, dones = rew.cpu().numpy(), dones.cpu().numpy()
+    for t in range(T):
+        cpu.step(actions[t])
+        assert np.array_equal(rew[t], cpu.rewards), f"step {t}: rewards"
+        assert np.array_equal(dones[t], cpu.dones), f"step {t}: dones"
+        for k in gu.OBS_KEYS:
+            assert np.array_equal(obs[k][t].astype(np.int32), cpu.obs[k].astype(np.int32)), f"step {t}: obs {k}"
+    same_state(gpu, cpu, "after the launch")
+    assert np.array_equal(gpu.stats.cpu().numpy(), cpu.stats)
+
+
+@pytest.mark.parametrize("size,n,p", [("small", 4099, 0.0), ("medium", 1000, 0.25), ("large", 515, 0.1)])
+def test_multi_step_greedy_equals_single_launches(size, n, p):
+    """wh_multi_step with the in-kernel greedy solver, auto-reset and observations written every step over
+    the resident tensors == the same number of wh_greedy_step launches: state, last observations
+    (reset-flavour for envs that just finished), last dones, per-agent reward sums, statistics — across two
+    episode boundaries, in chunks whose ends fall before, on and after an episode end."""
+    from rllib_warehouse_b200 import VARIANTS, BatchedWarehouse
+    cfg = VARIANTS[size].replace(random_num_agents=True)
+    one = BatchedWarehouse(cfg, n, seed=31, auto_reset=True)
+    many = BatchedWarehouse(cfg, n, seed=31, auto_reset=True)
+    one.reset(); many.reset()
+    for chunk in (1, 150, 49, 200, 7):                       # ends at t = 1, 151, 200 (episode end), 400, 407
+        total = torch.zeros((n, one.R), device=one.device)
+        for _ in range(chunk):
+            _, r, _ = one.greedy_step(random_action_prob=p, solver_seed=5)
+            total += r
+        _, sums, dones = many.multi_step(chunk, random_action_prob=p, solver_seed=5)
+        assert torch.equal(sums, total), chunk
+        assert torch.equal(dones, one.dones), chunk
+        for k in one.state:
+            assert torch.equal(one.state[k], many.state[k]), (chunk, k)
+        for k in one.obs:
+            assert torch.equal(one.obs[k], many.obs[k]), (chunk, k)
+    assert torch.equal(one.stats, many.stats) and int(one.stats[0]) == 2 * n

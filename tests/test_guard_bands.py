@@ -7,7 +7,7 @@ import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
-GUARD = 512
+GUARD = 1 << 16     # wide enough to catch a write one whole warp-tile past the end (dead tail warps)
 
 
 def rehome(env):
@@ -56,7 +56,11 @@ def test_no_out_of_bounds_writes(n):
             env.step(env.greedy_actions(random_action_prob=0.3, solver_seed=1))
             env.greedy_step(random_action_prob=0.2)
             env.build_obs_flat()
+            env.step_flat(a)
             env.build_obs(t % 2)
+            if t % 8 == 0:
+                env.multi_step(3)                                          # greedy, observations every step
+                env.multi_step(2, actions=rng.integers(-1, 9, size=(2, n, env.R)).astype(np.int32))
         env.reset(env_mask=(rng.random(n) < 0.5).astype(np.uint8))
         torch.cuda.synchronize()
         assert guards_intact(arenas), cfg
