@@ -78,6 +78,14 @@ typedef struct wh_obs {
     int32_t *requests;               /* [N,R,R,4]   16-byte aligned */
 } wh_obs;
 
+/* Render-only mirrors of the state as it was BEFORE the last step (core.py:160-163, 270-272):
+ * Warehouse.render(animate=True) interpolates from them (core.py:448-462). */
+typedef struct wh_prev {
+    int8_t *agent_pos;      /* [N,R,2]  _prev_agent_positions        core.py:161 */
+    int8_t *agent_tgt;      /* [N,R]    _prev_agent_delivery_targets core.py:162 */
+    int8_t *pickup_tgt;     /* [N,P]    _prev_pickup_point_targets   core.py:163 */
+} wh_prev;
+
 #define WH_OBS_STEP  0   /* core.py:371-432 */
 #define WH_OBS_RESET 1   /* core.py:224-260 */
 
@@ -115,19 +123,21 @@ int wh_reset(const wh_config *cfg, const wh_state *st, int64_t n_envs, int64_t e
 /* Warehouse.step — core.py:262-368,435-440; fused with the observation build (core.py:371-432)
  * when obs != NULL. actions [N,R] int32; order [N,R] = agent ids in action-dict iteration order,
  * -1 padded (NULL = ascending, core.py:279); spawn_pickups / spawn_targets [N,R] replayed respawn
- * draws, -1 padded (NULL = native RNG); rewards [N,R] f32; dones [N] u8; stats may be NULL. */
+ * draws, -1 padded (NULL = native RNG); rewards [N,R] f32; dones [N] u8; stats may be NULL.
+ * env_mask [N] u8 or NULL: only envs with a non-zero entry are stepped; the others keep their state,
+ * observation, rewards and dones untouched (a BaseEnv.send_actions() that covers a subset of the envs). */
 int wh_step(const wh_config *cfg, const wh_state *st, int64_t n_envs, int64_t env_id0, uint64_t seed,
             const int32_t *actions, const int32_t *order,
             const int8_t *spawn_pickups, const int8_t *spawn_targets,
             float *rewards, uint8_t *dones, unsigned long long *stats,
-            const wh_obs *obs, int flags, void *stream);
+            const wh_obs *obs, int flags, const uint8_t *env_mask, void *stream);
 
 /* wh_step with the observations emitted directly in RLlib's flattened float32 layout
  * (see wh_build_obs_flat) by the same kernel — the path a vectorised RLlib sampler consumes.
  * flat_obs [N, R, 9R+1] float32. With WH_FLAG_AUTO_RESET finished envs get their reset observation. */
 int wh_step_flat(const wh_config *cfg, const wh_state *st, int64_t n_envs, int64_t env_id0, uint64_t seed,
                  const int32_t *actions, const int32_t *order, float *rewards, uint8_t *dones,
-                 unsigned long long *stats, float *flat_obs, int flags, void *stream);
+                 unsigned long long *stats, float *flat_obs, int flags, const uint8_t *env_mask, void *stream);
 
 /* Observation build alone — flavour WH_OBS_STEP (core.py:371-432) or WH_OBS_RESET (core.py:224-260). */
 int wh_build_obs(const wh_config *cfg, const wh_state *st, int64_t n_envs, int flavour,
@@ -182,6 +192,11 @@ int wh_multi_step(const wh_config *cfg, const wh_state *st, int64_t n_envs, int6
                   int n_steps, const int32_t *actions, uint64_t solver_seed, uint64_t rand_threshold,
                   float *rewards, uint8_t *dones, unsigned long long *stats, const wh_obs *obs, int flags,
                   void *stream);
+
+/* core.py:270-272 — keep the render-only `_prev_*` mirrors: copies agent positions, agent delivery
+ * targets and pickup-point targets into `prev` on `stream` (device-to-device, no synchronisation). A caller
+ * that wants Warehouse.render(animate=True) issues it right before wh_step; nobody else pays for it. */
+int wh_save_prev(const wh_config *cfg, const wh_state *st, const wh_prev *prev, int64_t n_envs, void *stream);
 
 /* End-of-rollout reduction of the episode statistics over NVLink: in-place ncclAllReduce(sum) of the
  * WH_NUM_STATS uint64 counters on `stream`. `nccl_comm` is a ncclComm_t created by the caller with

@@ -13,11 +13,12 @@ from .variants import (WarehouseLarge, WarehouseLargeTrain, WarehouseMedium, War
 from .solvers import BatchedGreedySolver, WarehouseRandomGreedySolver, WarehouseSolver
 from .vector_env import WarehouseVectorEnv
 from .host_env import HostWarehouse
+from .sampler import RolloutSampler, mlp_policy
 
 __all__ = [
     "Warehouse", "WarehouseSmall", "WarehouseMedium", "WarehouseLarge",
     "WarehouseSmallTrain", "WarehouseMediumTrain", "WarehouseLargeTrain",
     "WarehouseConfig", "SMALL", "MEDIUM", "LARGE", "VARIANTS",
-    "BatchedWarehouse", "StepGraph", "HostWarehouse", "WarehouseVectorEnv", "BatchedGreedySolver", "WarehouseRandomGreedySolver", "WarehouseSolver",
+    "BatchedWarehouse", "StepGraph", "HostWarehouse", "WarehouseVectorEnv", "RolloutSampler", "mlp_policy", "BatchedGreedySolver", "WarehouseRandomGreedySolver", "WarehouseSolver",
 ]
 name = "rllib_warehouse_b200"

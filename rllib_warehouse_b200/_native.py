@@ -23,7 +23,7 @@ STATE_KEYS = ("agent_pos", "agent_tgt", "pickup_tgt", "pickup_timer", "time", "n
 # every symbol include/wh_b200.h declares
 SYMBOLS = (
     "wh_version", "wh_error_string", "wh_num_pickup_points", "wh_num_delivery_points",
-    "wh_reset", "wh_step", "wh_step_flat", "wh_build_obs", "wh_build_obs_flat", "wh_greedy", "wh_greedy_step", "wh_greedy_rollout", "wh_multi_step", "wh_stats_allreduce",
+    "wh_reset", "wh_step", "wh_step_flat", "wh_build_obs", "wh_build_obs_flat", "wh_greedy", "wh_greedy_step", "wh_greedy_rollout", "wh_multi_step", "wh_save_prev", "wh_stats_allreduce",
     "wh_env_create", "wh_env_destroy", "wh_env_reset", "wh_env_step_host", "wh_env_step_host_compact", "wh_env_greedy_step_host",
     "wh_env_obs_ptrs", "wh_env_state_ptrs", "wh_env_stats_host", "wh_env_launch_count",
 )
@@ -46,6 +46,10 @@ class State(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in STATE_KEYS]
 
 
+class Prev(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("agent_pos", "agent_tgt", "pickup_tgt")]
+
+
 class Obs(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in OBS_KEYS]
 
@@ -66,8 +70,8 @@ def lib():
         L.wh_env_launch_count.restype = C.c_int64
         vp, i64, u64, ci = C.c_void_p, C.c_int64, C.c_uint64, C.c_int
         L.wh_reset.argtypes = [vp, vp, i64, i64, u64, vp, vp, vp, vp, vp, vp, vp]
-        L.wh_step.argtypes = [vp, vp, i64, i64, u64, vp, vp, vp, vp, vp, vp, vp, vp, ci, vp]
-        L.wh_step_flat.argtypes = [vp, vp, i64, i64, u64, vp, vp, vp, vp, vp, vp, ci, vp]
+        L.wh_step.argtypes = [vp, vp, i64, i64, u64, vp, vp, vp, vp, vp, vp, vp, vp, ci, vp, vp]
+        L.wh_step_flat.argtypes = [vp, vp, i64, i64, u64, vp, vp, vp, vp, vp, vp, ci, vp, vp]
         L.wh_greedy_step.argtypes = [vp, vp, i64, i64, u64, u64, u64, vp, vp, vp, vp, vp, ci, vp]
         L.wh_greedy_rollout.argtypes = [vp, vp, i64, i64, u64, u64, u64, ci, vp, vp, vp, ci, vp]
         L.wh_multi_step.argtypes = [vp, vp, i64, i64, u64, ci, vp, u64, u64, vp, vp, vp, vp, ci, vp]
@@ -75,6 +79,7 @@ def lib():
         L.wh_build_obs_flat.argtypes = [vp, vp, i64, ci, vp, vp]
         L.wh_greedy.argtypes = [vp, vp, vp, vp, vp, i64, i64, u64, u64, vp, vp, vp, vp]
         L.wh_stats_allreduce.argtypes = [vp, vp, vp]
+        L.wh_save_prev.argtypes = [vp, vp, vp, i64, vp]
         L.wh_env_create.argtypes = [vp, i64, ci, i64, u64, ci, vp]
         L.wh_env_destroy.argtypes = [vp]
         L.wh_env_destroy.restype = None

@@ -146,8 +146,25 @@ class BatchedWarehouse:
         self._st = nv.State(**{k: self.state[k].data_ptr() for k in nv.STATE_KEYS})
         self._ob = nv.Obs(**{k: self.obs[k].data_ptr() for k in OBS_KEYS})
         self.launches = 0
+        self.prev = None                         # render-only `_prev_*` mirrors (core.py:160-163), see track_prev()
 
     # ------------------------------------------------------------------------------------------
+    def track_prev(self, on=True):
+        """Keep the reference's render-only `_prev_*` state (core.py:270-272): every step first copies agent
+        positions / delivery targets and pickup-point targets aside (three device-to-device copies, no
+        synchronisation). Off by default — only `Warehouse.render(animate=True)` reads them."""
+        if on and self.prev is None:
+            self.prev = {k: self.state[k].clone() for k in ("agent_pos", "agent_tgt", "pickup_tgt")}
+            self._pv = nv.Prev(**{k: v.data_ptr() for k, v in self.prev.items()})
+        elif not on:
+            self.prev = None
+
+    def _save_prev(self):
+        if self.prev is not None:
+            with self._on_device:
+                rc = self.lib.wh_save_prev(C.byref(self._cfg), C.byref(self._st), C.byref(self._pv), self.N, self._stream())
+            nv.check(rc, "wh_save_prev")
+
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
@@ -179,41 +196,47 @@ class BatchedWarehouse:
         nv.check(rc, "wh_reset")
         self.launches += 1
         del keep
+        self._save_prev()                        # core.py:203-213: after a reset the mirrors equal the fresh state
         return self.obs
 
-    def step(self, actions, order=None, spawn_pickups=None, spawn_targets=None, with_obs=True):
-        """core.py:262-442. actions [N,R] int (-1 = agent absent); order [N,R] = action-dict order."""
+    def step(self, actions, order=None, spawn_pickups=None, spawn_targets=None, with_obs=True, env_mask=None):
+        """core.py:262-442. actions [N,R] int (-1 = agent absent); order [N,R] = action-dict order.
+        env_mask [N] (non-zero = step this env): the other envs keep state, observation, reward, done."""
         dev, N, R = self.device, self.N, self.R
         actions = _dev_tensor(actions, torch.int32, dev, (N, R))
         order = _dev_tensor(order, torch.int32, dev, (N, R))
         spawn_pickups = _dev_tensor(spawn_pickups, torch.int8, dev, (N, R))
         spawn_targets = _dev_tensor(spawn_targets, torch.int8, dev, (N, R))
+        env_mask = _dev_tensor(env_mask, torch.uint8, dev, (N,))
         flags = nv.FLAG_AUTO_RESET if (self.auto_reset and spawn_pickups is None) else 0
+        self._save_prev()                        # core.py:270-272
         with self._on_device:
             rc = self.lib.wh_step(C.byref(self._cfg), C.byref(self._st), N, self.env_id0, self.seed,
                                   _ptr(actions), _ptr(order), _ptr(spawn_pickups), _ptr(spawn_targets),
                                   self.rewards.data_ptr(), self.dones.data_ptr(), self.stats.data_ptr(),
-                                  C.byref(self._ob) if with_obs else None, flags, self._stream())
+                                  C.byref(self._ob) if with_obs else None, flags, _ptr(env_mask), self._stream())
         nv.check(rc, "wh_step")
         self.launches += 1
         return self.obs, self.rewards, self.dones
 
-    def step_flat(self, actions, order=None, out=None):
+    def step_flat(self, actions, order=None, out=None, env_mask=None):
         """`step` whose observations are RLlib-flattened float32 [N, R, 9R+1], written by the step
         kernel itself (no dict-keyed tensors are produced)."""
         dev, N, R = self.device, self.N, self.R
         actions = _dev_tensor(actions, torch.int32, dev, (N, R))
         order = _dev_tensor(order, torch.int32, dev, (N, R))
+        env_mask = _dev_tensor(env_mask, torch.uint8, dev, (N,))
         if out is None:
             if getattr(self, "_flat", None) is None:
                 self._flat = torch.empty((N, R, 9 * R + 1), dtype=torch.float32, device=dev)
             out = self._flat
         flags = nv.FLAG_AUTO_RESET if self.auto_reset else 0
+        self._save_prev()                        # core.py:270-272
         with self._on_device:
             rc = self.lib.wh_step_flat(C.byref(self._cfg), C.byref(self._st), N, self.env_id0, self.seed,
                                        _ptr(actions), _ptr(order), self.rewards.data_ptr(),
                                        self.dones.data_ptr(), self.stats.data_ptr(), out.data_ptr(),
-                                       flags, self._stream())
+                                       flags, _ptr(env_mask), self._stream())
         nv.check(rc, "wh_step_flat")
         self.launches += 1
         return out, self.rewards, self.dones
@@ -223,6 +246,7 @@ class BatchedWarehouse:
         (solvers.py:27-58) evaluated from the resident state, then step + observation build."""
         thr = int(float(random_action_prob) * 4294967296.0)
         flags = nv.FLAG_AUTO_RESET if self.auto_reset else 0
+        self._save_prev()                        # core.py:270-272
         with self._on_device:
             rc = self.lib.wh_greedy_step(C.byref(self._cfg), C.byref(self._st), self.N, self.env_id0,
                                          self.seed, int(solver_seed), thr,

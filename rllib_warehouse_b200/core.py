@@ -8,6 +8,7 @@ work unchanged. One instance drives a 1-env `BatchedWarehouse`; this compatibili
 device->host copy per step and is NOT the throughput path (that is `BatchedWarehouse` /
 `WarehouseVectorEnv`, which keep everything on the GPU).
 """
+import time
 from typing import Dict, List, Tuple
 
 import numpy as np
@@ -114,15 +115,30 @@ class Warehouse(MultiAgentEnv):
         return obs, rewards, dones, {str(i): {} for i in range(A)}
 
     def render(self, mode: str = "human", animate: bool = False) -> None:
-        """core.py:444-617 draws env state with gym's pyglet viewer (agents, pickup racks, delivery
-        points, optional 10-frame interpolation). pyglet / a display are not available in this
-        image, so the bridge copies env-0 state to the host (`render_state`) and prints a text
-        frame with the same information: `.` floor, `p`/`P` idle/waiting pickup point, `d`/`D`
-        idle/targeted delivery point, digits = free agents, letters a.. = delivering agents.
-        `animate` is accepted for signature compatibility and ignored."""
+        """core.py:444-475. Copies env state (and the `_prev_*` mirrors, core.py:270-272) to the host and
+        draws it like the reference: through gym's pyglet viewer when `gym.envs.classic_control.rendering`
+        imports, else the frame's primitives are recorded (`self._viewer.frames`) and a text frame is
+        printed: `.` floor, `p`/`P` idle/waiting pickup point, `d`/`D` idle/targeted delivery point,
+        digits = free agents, letters a.. = delivering agents. With `animate`, 10 frames interpolated from
+        the previous step's positions, paced to 6 steps per second (core.py:448-470)."""
         if mode != "human":
             raise NotImplementedError(f"render mode {mode!r}")                 # core.py:445-446
-        print(self.render_text())
+        from . import render as rd
+        if self._viewer is None:
+            self._viewer = rd.make_viewer(self._config.area_dimension)        # core.py:480-485
+        if not self._batched.prev:
+            # from now on every step keeps the previous state aside, as the reference always does; until the
+            # next step the mirrors equal the current state (exactly the reference's situation after reset)
+            self._batched.track_prev(True)
+        cfg = self._config
+        recorder = isinstance(self._viewer, rd.PrimitiveRecorder)
+        if recorder:
+            self._viewer.clear()
+        rd.draw(self._viewer, cfg.area_dimension, cfg.pickup_racks_arrangement, self.render_state(), animate,
+                self.animate_frames_per_step, self.animate_steps_per_second,
+                sleep=(lambda s: None) if recorder else time.sleep)
+        if recorder:
+            print(self.render_text())
 
     def render_text(self) -> str:
         st = self.render_state()
@@ -144,8 +160,20 @@ class Warehouse(MultiAgentEnv):
         return f"t={st['episode_time']}\n" + "\n".join(rows)
 
     def render_state(self) -> Dict[str, np.ndarray]:
+        """Everything `render` reads (core.py:452-475), as the reference's int32 arrays: the current state
+        and the `_prev_*` mirrors (equal to the current state until prev tracking has seen a step)."""
         st = self._batched.get_state()
         A = self.num_agents
-        return dict(agent_positions=st["agent_pos"][0, :A], agent_delivery_targets=st["agent_tgt"][0, :A],
-                    pickup_point_targets=st["pickup_tgt"][0], pickup_point_timers=st["pickup_timer"][0],
-                    episode_time=int(st["time"][0]))
+        out = dict(agent_positions=st["agent_pos"][0, :A], agent_delivery_targets=st["agent_tgt"][0, :A],
+                   pickup_point_targets=st["pickup_tgt"][0], pickup_point_timers=st["pickup_timer"][0],
+                   episode_time=int(st["time"][0]))
+        prev = self._batched.prev
+        if prev:
+            out.update(prev_agent_positions=prev["agent_pos"][0, :A].to(torch.int32).cpu().numpy(),
+                       prev_agent_delivery_targets=prev["agent_tgt"][0, :A].to(torch.int32).cpu().numpy(),
+                       prev_pickup_point_targets=prev["pickup_tgt"][0].to(torch.int32).cpu().numpy())
+        else:
+            out.update(prev_agent_positions=out["agent_positions"].copy(),
+                       prev_agent_delivery_targets=out["agent_delivery_targets"].copy(),
+                       prev_pickup_point_targets=out["pickup_point_targets"].copy())
+        return out

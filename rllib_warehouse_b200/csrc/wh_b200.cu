@@ -117,10 +117,12 @@ __global__ void __launch_bounds__(BLOCK, (RC == 16 ? WH_MIN_BLOCKS_LARGE : RC ==
     asm volatile("griddepcontrol.wait;" ::: "memory");
     load_env(P, g, e, R, (RC ? 4 * GC : P.P), s);
 
+    // envs masked out of this step (BaseEnv.send_actions for a subset of the envs) compute along but write nothing
+    const bool live = t.live && (PLAIN || !P.env_mask || P.env_mask[e] != 0);
     int act = -1, ord = -1;
     if (GREEDY) {
         act = greedy_from_state<GC, RC>(P, g, R, env_id, s);
-        if (P.actions_out && t.live && g.gl < R) P.actions_out[e * R + g.gl] = act;
+        if (P.actions_out && live && g.gl < R) P.actions_out[e * R + g.gl] = act;
     } else if (g.gl < R) {
         act = (!PLAIN && (P.flags & WH_FLAG_COMPACT_IO)) ? (int)reinterpret_cast<const int8_t *>(P.actions)[e * R + g.gl]
                                                           : P.actions[e * R + g.gl];
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(BLOCK, (RC == 16 ? WH_MIN_BLOCKS_LARGE : RC ==
     uint32_t tpos16 = so.tpos16;
 
     const bool done = s.time >= P.episode;                                     // core.py:438
-    if (t.live) {
+    if (live) {
         if (g.gl < R) {                                                         // core.py:435
             if (!PLAIN && (P.flags & WH_FLAG_COMPACT_IO)) reinterpret_cast<uint8_t *>(P.rewards)[e * R + g.gl] = (uint8_t)so.reward;
             else P.rewards[e * R + g.gl] = so.reward;
@@ -141,21 +143,21 @@ __global__ void __launch_bounds__(BLOCK, (RC == 16 ? WH_MIN_BLOCKS_LARGE : RC ==
         if (g.gl == 0) P.dones[e] = done ? 1 : 0;
     }
     const bool auto_reset = (P.flags & WH_FLAG_AUTO_RESET) != 0;
-    account_episode(P, g.gl == 0 && t.live, e, so, s, done, auto_reset);
+    account_episode(P, g.gl == 0 && live, e, so, s, done, auto_reset);
     int flavour = WH_OBS_STEP;
     bool meta = false;
     if (auto_reset && __any_sync(FULL, done)) {
-        const unsigned long long a2 = do_reset(P, g, e, R, env_id, s, false, done && t.live);
+        const unsigned long long a2 = do_reset(P, g, e, R, env_id, s, false, done && live);
         if (done) { active = a2; flavour = WH_OBS_RESET; }
         meta = true;
     }
-    if (t.live) store_env(P, g, e, R, (RC ? 4 * GC : P.P), s, meta);
+    if (live) store_env(P, g, e, R, (RC ? 4 * GC : P.P), s, meta);
     if constexpr (FLAT)   // RLlib-flattened float32 layout instead of the dict keys (separate instantiation)
-        build_obs_flat<GC, RC>(P, g, e, R, s, active, tpos16, flavour, t.live, P.flat_out,
+        build_obs_flat<GC, RC>(P, g, e, R, s, active, tpos16, flavour, live, P.flat_out,
                                reinterpret_cast<float *>(StageMem<GC, RC, true>::mine(smem, g)),
                                reinterpret_cast<float *>(StageMem<GC, RC, true>::warp_area(smem)), t.env0);
     else if (P.obs.requests)
-        build_obs<GC, RC>(P, P.obs, g, e, R, s, active, tpos16, flavour, t.live, StageMem<GC, RC>::mine(smem, g),
+        build_obs<GC, RC>(P, P.obs, g, e, R, s, active, tpos16, flavour, live, StageMem<GC, RC>::mine(smem, g),
                           StageMem<GC, RC>::warp_area(smem), t.env0);
 }
 
@@ -489,7 +491,7 @@ static void launch_kind(Kind kind, const KParams &K, cudaStream_t s) {
             done[dev].store(true, std::memory_order_release);
         }
     }
-    const bool plain = RC != 0 && !(K.flags & WH_FLAG_COMPACT_IO) && !K.order && !K.spawn_p;
+    const bool plain = RC != 0 && !(K.flags & WH_FLAG_COMPACT_IO) && !K.order && !K.spawn_p && !K.env_mask;
     switch (kind) {
     case K_STEP:
         if (plain) launch_step(k_step<GC, RC, false, false, RC != 0>, grid, dyn, s, K);
@@ -586,12 +588,14 @@ static int launch(Kind kind, const KParams &K, const Shape &sh, void *stream) {
 
 using namespace wh;
 
+#define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return (int)_e; } while (0)
+
 // ---------------------------------------------------------------------------------------------
 // C ABI — layer 1
 // ---------------------------------------------------------------------------------------------
 extern "C" {
 
-int wh_version(void) { return 100; }
+int wh_version(void) { return 101; }
 
 const char *wh_error_string(int code) {
     if (code == 0) return "ok";
@@ -625,11 +629,12 @@ int wh_step(const wh_config *cfg, const wh_state *st, int64_t n_envs, int64_t en
             const int32_t *actions, const int32_t *order,
             const int8_t *spawn_pickups, const int8_t *spawn_targets,
             float *rewards, uint8_t *dones, unsigned long long *stats,
-            const wh_obs *obs, int flags, void *stream) {
+            const wh_obs *obs, int flags, const uint8_t *env_mask, void *stream) {
     KParams K; Shape sh;
     if (int rc = fill_params(cfg, K, sh)) return rc;
     if (n_envs == 0) return 0;   // empty batch: nothing to launch
     if (!state_ok(st) || !actions || !rewards || !dones || (obs && !obs_ok(obs))) return WH_E_ARG;
+    K.env_mask = env_mask;
     if ((spawn_pickups == nullptr) != (spawn_targets == nullptr)) return WH_E_ARG;
     if ((flags & WH_FLAG_AUTO_RESET) && spawn_pickups) return WH_E_ARG;  // auto-reset needs the native RNG
     set_state(K, st);
@@ -642,11 +647,12 @@ int wh_step(const wh_config *cfg, const wh_state *st, int64_t n_envs, int64_t en
 
 int wh_step_flat(const wh_config *cfg, const wh_state *st, int64_t n_envs, int64_t env_id0, uint64_t seed,
                  const int32_t *actions, const int32_t *order, float *rewards, uint8_t *dones,
-                 unsigned long long *stats, float *flat_obs, int flags, void *stream) {
+                 unsigned long long *stats, float *flat_obs, int flags, const uint8_t *env_mask, void *stream) {
     KParams K; Shape sh;
     if (int rc = fill_params(cfg, K, sh)) return rc;
     if (n_envs == 0) return 0;   // empty batch: nothing to launch
     if (!state_ok(st) || !actions || !rewards || !dones || !flat_obs) return WH_E_ARG;
+    K.env_mask = env_mask;
     set_state(K, st);
     K.flat_out = flat_obs;
     K.N = n_envs; K.env_id0 = env_id0; K.seed = seed;
@@ -743,6 +749,19 @@ int wh_greedy(const wh_config *cfg, const wh_obs *obs, const int8_t *num_agents,
     return launch(K_GREEDY, K, sh, stream);
 }
 
+int wh_save_prev(const wh_config *cfg, const wh_state *st, const wh_prev *prev, int64_t n_envs, void *stream) {
+    KParams K; Shape sh;
+    if (int rc = fill_params(cfg, K, sh)) return rc;
+    if (n_envs == 0) return 0;
+    if (!state_ok(st) || !prev || !prev->agent_pos || !prev->agent_tgt || !prev->pickup_tgt) return WH_E_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    // core.py:270-272: copies taken at the top of step(), used only by render(animate=True)
+    CK(cudaMemcpyAsync(prev->agent_pos, st->agent_pos, (size_t)n_envs * K.R * 2, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(prev->agent_tgt, st->agent_tgt, (size_t)n_envs * K.R, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(prev->pickup_tgt, st->pickup_tgt, (size_t)n_envs * K.P, cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
 int wh_stats_allreduce(unsigned long long *stats, void *nccl_comm, void *stream) {
     if (!stats || !nccl_comm) return WH_E_ARG;
     // ncclResult_t ncclAllReduce(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t)
@@ -780,8 +799,6 @@ struct wh_env {
     cudaStream_t *streams;
     int64_t launches;
 };
-
-#define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return (int)_e; } while (0)
 
 static wh_state offset_state(const wh_env *E, int64_t e0) {
     wh_state s = E->st;
@@ -897,12 +914,12 @@ static int env_step_issue(wh_env *E, const int32_t *actions, float *rewards, uin
                 CK(cudaMemcpyAsync(da, reinterpret_cast<const int8_t *>(actions) + e0 * R, n * R, cudaMemcpyHostToDevice, s));
                 rc = wh_step(&E->cfg, &st, n, E->env_id0 + e0, E->seed, reinterpret_cast<const int32_t *>(da), nullptr,
                              nullptr, nullptr, reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(E->d_rewards) + e0 * R),
-                             E->d_dones + e0, E->d_stats, &ob, WH_FLAG_AUTO_RESET | WH_FLAG_COMPACT_IO | WH_FLAG_NO_PDL, s);
+                             E->d_dones + e0, E->d_stats, &ob, WH_FLAG_AUTO_RESET | WH_FLAG_COMPACT_IO | WH_FLAG_NO_PDL, nullptr, s);
             } else {
                 CK(cudaMemcpyAsync(E->d_actions + e0 * R, actions + e0 * R, n * R * 4, cudaMemcpyHostToDevice, s));
                 rc = wh_step(&E->cfg, &st, n, E->env_id0 + e0, E->seed, E->d_actions + e0 * R, nullptr, nullptr,
                              nullptr, E->d_rewards + e0 * R, E->d_dones + e0, E->d_stats, &ob,
-                             WH_FLAG_AUTO_RESET | WH_FLAG_NO_PDL, s);
+                             WH_FLAG_AUTO_RESET | WH_FLAG_NO_PDL, nullptr, s);
             }
         }
         E->launches += 1;

@@ -881,45 +881,59 @@ __device__ __forceinline__ void build_obs_flat(const KParams &P, const Group<GC>
         }
         __syncwarp();
         // ---- copy-out: the warp's EPW environments are ONE contiguous range of the output; all 32 lanes
-        // stream it with 128-bit stores, every float fetched through the static map ----
+        // stream it with 128-bit stores, every float fetched through the static map. An environment that is
+        // not written (past N, or masked out of this step) keeps its observation: bit env*GC of `lm`.
         const uint8_t *map = flat_map<RC>();
-        const uint32_t n = (uint32_t)P.N;
-        const int n_live = (env0 + EPW <= n) ? EPW : (int)(n - env0);        // k_step / k_obs_flat: a prefix
-        const int limit = (env0 < n) ? n_live * M::RF : 0;                   // floats of this warp
+        const uint32_t lm = __ballot_sync(FULL, live);
+        auto env_live = [&](int env) { return ((lm >> (env * GC)) & 1u) != 0u; };
+        constexpr int TOT = EPW * M::RF;                                     // floats of this warp
         float *wout = out + (size_t)env0 * M::RF;
         const int head = (M::RF % 4 == 0) ? 0 : (int)((0u - env0 * (uint32_t)M::RF) & 3u);   // floats before the first 16-byte boundary (0 or 2)
-        auto fetch2 = [&](int k) -> float2 {             // floats k, k+1 of the warp's range (k even: never straddles an env)
-            int env = 0, kk = k;
+        auto locate = [&](int k, int &env, int &kk) {    // float k of the warp's range -> (environment, float in it)
+            env = 0; kk = k;
             if constexpr (EPW <= 3) {
 #pragma unroll
                 for (int t = 1; t < EPW; ++t) if (k >= t * M::RF) { env = t; kk = k - t * M::RF; }
             } else {
-                env = (int)(((uint32_t)k * (uint32_t)((65536 + M::RF - 1) / M::RF)) >> 16);   // k / RF for k < EPW*RF (checked below)
+                env = (int)(((uint32_t)k * (uint32_t)((65536 + M::RF - 1) / M::RF)) >> 16);   // k / RF (range checked below)
                 kk = k - env * M::RF;
             }
+        };
+        auto pair = [&](int env, int kk) -> float2 {     // floats kk, kk+1 of an environment (kk even)
             const uint32_t mm = *reinterpret_cast<const uint16_t *>(map + kk);
             const float *v = wstage + env * M::VS;
             return make_float2(v[mm & 0xFFu], v[mm >> 8]);
         };
         static_assert(M::RF % 2 == 0, "pairs never straddle environments");
         static_assert(EPW <= 3 || ((EPW * M::RF - 1) * ((65536 + M::RF - 1) / M::RF)) >> 16 == EPW - 1, "reciprocal division range");
-        const int nb = limit > head ? (limit - head) >> 2 : 0;               // whole float4 in the range (none for a warp past N)
-        constexpr int ITERS = (EPW * M::RF / 4 + 31) / 32;
+        constexpr int ITERS = (TOT / 4 + 31) / 32;
+        const int nb = (TOT - head) >> 2;                                    // whole float4 in the range
 #pragma unroll 4
         for (int it = 0; it < ITERS; ++it) {
             const int i = g.lane + 32 * it;
             if (i < nb) {
                 const int k = head + 4 * i;
-                const float2 a = fetch2(k), b = fetch2(k + 2);
-                WH_ST(reinterpret_cast<float4 *>(wout + k), make_float4(a.x, a.y, b.x, b.y));
+                int e0, k0, e1, k1;
+                locate(k, e0, k0);
+                if constexpr (M::RF % 4 == 0) { e1 = e0; k1 = k0 + 2; }
+                else locate(k + 2, e1, k1);
+                const bool l0 = env_live(e0), l1 = env_live(e1);
+                if (l0 && l1) {
+                    const float2 a = pair(e0, k0), b = pair(e1, k1);
+                    WH_ST(reinterpret_cast<float4 *>(wout + k), make_float4(a.x, a.y, b.x, b.y));
+                } else if (l0) {
+                    WH_ST(reinterpret_cast<float2 *>(wout + k), pair(e0, k0));
+                } else if (l1) {
+                    WH_ST(reinterpret_cast<float2 *>(wout + k + 2), pair(e1, k1));
+                }
             }
         }
-        if (M::RF % 4 != 0) {                                                // 8-byte head / tail of a misaligned range
-            if (g.lane == 0 && head == 2 && limit >= 2) WH_ST(reinterpret_cast<float2 *>(wout), fetch2(0));
+        if constexpr (M::RF % 4 != 0) {                                      // 8-byte head / tail of a misaligned range
+            if (g.lane == 0 && head == 2 && env_live(0)) WH_ST(reinterpret_cast<float2 *>(wout), pair(0, 0));
             const int tail = head + 4 * nb;
-            if (g.lane == 1 && limit > 0 && tail < limit) WH_ST(reinterpret_cast<float2 *>(wout + tail), fetch2(tail));
+            if (g.lane == 1 && tail < TOT && env_live(EPW - 1))
+                WH_ST(reinterpret_cast<float2 *>(wout + tail), pair(EPW - 1, tail - (EPW - 1) * M::RF));
         }
-        (void)live;
     } else {
         // runtime-R geometries: every lane writes its pieces of each agent row straight to global memory
         const uint32_t mine = (ppos & 0x7Fu) | (((ppos >> 8) & 0x7Fu) << 7) | ((tpos & 0x7Fu) << 14) |

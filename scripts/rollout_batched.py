@@ -34,18 +34,18 @@ def main(a):
     steps = a.episodes * cfg.episode_duration
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    flavour_reset = True
     with torch.no_grad():
-        for _ in range(steps):
-            if policy is None:
-                env.greedy_step(random_action_prob=a.random_action_prob, solver_seed=a.seed + 1,
-                                want_actions=False)
-            else:
-                flat = env.build_obs_flat(1 if flavour_reset else 0)
+        if policy is None:
+            for _ in range(steps):
+                env.greedy_step(random_action_prob=a.random_action_prob, solver_seed=a.seed + 1, want_actions=False)
+        else:
+            # one launch per step: the step kernel itself emits the RLlib-flattened observations the policy
+            # reads (reset-flavour ones for envs that were just auto-reset); nothing is synchronised per step
+            flat = env.build_obs_flat(1)
+            for _ in range(steps):
                 logits = policy(flat.view(-1, flat.shape[-1]))
                 actions = logits.argmax(dim=-1).view(env.N, env.R).to(torch.int32)
-                _, _, dones = env.step(actions, with_obs=False)
-                flavour_reset = bool(dones[0].item())   # envs run in lock-step (fixed episode length)
+                flat, _, _ = env.step_flat(actions)
     stats = allreduce_stats(env.stats)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0

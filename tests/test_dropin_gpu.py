@@ -208,3 +208,78 @@ def test_host_warehouse_numpy_api(compact):
         assert torch.equal(v, twin.obs[k]), k
     assert np.array_equal(host.stats(), twin.stats.cpu().numpy())
     host.close()
+
+
+def test_vector_env_partial_send_actions_and_action_validation():
+    """BaseEnv contract: only the envs named in send_actions advance (the others keep state, time and
+    observations — env_mask of wh_step); actions are indices into MOVES (core.py:38,282): -9..-1 wrap like a
+    Python list index, anything else raises IndexError; agent ids outside the env's agents raise too."""
+    import torch
+    from rllib_warehouse_b200 import MEDIUM, BatchedWarehouse, WarehouseVectorEnv
+    n, A = 9, 4
+    for flat in (False, True):
+        venv = WarehouseVectorEnv(MEDIUM, n, num_agents=A, seed=5, flat_obs=flat)
+        twin = BatchedWarehouse(MEDIUM, n, num_agents=A, seed=5)
+        twin.reset()
+        venv.poll()
+        rng = np.random.Generator(np.random.PCG64(1))
+        for t in range(25):
+            chosen = sorted(rng.choice(n, size=int(rng.integers(1, n + 1)), replace=False).tolist())
+            acts = {e: {str(i): int(rng.integers(-9, 9)) for i in range(A)} for e in chosen}
+            venv.send_actions(acts)
+            a = np.full((n, twin.R), -1, np.int32)
+            mask = np.zeros(n, np.uint8)
+            for e in chosen:
+                mask[e] = 1
+                for ag, v in acts[e].items():
+                    a[e, int(ag)] = v % 9                                     # Python list index wrap (core.py:282)
+            before = {k: v.clone() for k, v in twin.state.items()}
+            twin.step(a, env_mask=mask)
+            keep = torch.from_numpy(mask == 0).cuda()
+            for k in before:                                                   # masked-out envs did not move in time
+                assert torch.equal(twin.state[k][keep], before[k][keep]), k
+            obs, rew, dones, _, _ = venv.poll()
+            assert sorted(obs) == chosen
+            for k in twin.state:
+                assert torch.equal(venv.env.state[k], twin.state[k]), (t, k)
+            for e in chosen:
+                for i in range(A):
+                    assert rew[e][str(i)] == twin.rewards[e, i].item()
+                    if flat:
+                        want = twin.build_obs_flat()[e, i].cpu().numpy()
+                        assert np.array_equal(obs[e][str(i)], want), (t, e, i)
+                    else:
+                        assert all(np.array_equal(obs[e][str(i)][k], twin.obs[k][e, i].cpu().numpy()) for k in twin.obs)
+        assert int(venv.env.state["time"].min()) < int(venv.env.state["time"].max())   # envs really desynchronised
+        with pytest.raises(IndexError):
+            venv.send_actions({0: {"0": 9}})
+        with pytest.raises(IndexError):
+            venv.send_actions({0: {"0": -10}})
+        with pytest.raises(IndexError):
+            venv.send_actions({0: {str(A): 0}})
+        with pytest.raises(IndexError):
+            venv.send_actions({n: {"0": 0}})
+        assert venv.action_space.n == 9
+        assert venv.observation_space.shape == (9 * 9 + 1,) if flat else venv.observation_space.contains(
+            {k: twin.obs[k][0, 0].cpu().numpy() for k in twin.obs})
+
+
+def test_rollout_sampler_through_the_base_env_adapter():
+    """The ray-free sampler loop (RolloutSampler) drives WarehouseVectorEnv strictly through poll /
+    send_actions / try_reset with a torch policy, across episode ends with per-env agent counts (*Train);
+    the tensor mode (reset_tensors / step_tensors, in-kernel auto-reset) sees the same environment: both
+    modes produce the same per-episode returns for the same policy and seed."""
+    import torch
+    from rllib_warehouse_b200 import SMALL, RolloutSampler, WarehouseVectorEnv, mlp_policy
+    cfg = SMALL.replace(random_num_agents=True, episode_duration=15)
+    n, iters = 48, 47                                            # 3 episodes and 2 steps
+    policy = mlp_policy(9 * cfg.num_requests + 1, hidden=32, device="cuda:0", seed=3)
+    a = RolloutSampler(WarehouseVectorEnv(cfg, n, seed=11, flat_obs=True), policy)
+    ra = a.run_base_env(iters)
+    b = RolloutSampler(WarehouseVectorEnv(cfg, n, seed=11, flat_obs=True, auto_reset=True), policy)
+    rb = b.run_tensor(iters)
+    assert ra["env_steps"] == rb["env_steps"] == n * iters
+    assert len(a.episode_returns) == len(b.episode_returns) == 3 * n
+    assert np.allclose(sorted(a.episode_returns), sorted(b.episode_returns))
+    assert ra["agent_steps"] < n * cfg.num_requests * iters       # fewer than R agents in many envs (*Train)
+    assert max(a.episode_returns) > 0

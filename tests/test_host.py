@@ -32,7 +32,7 @@ def test_config_and_argument_validation_needs_no_gpu():
     assert L.wh_num_pickup_points(C.byref(cfg)) == 64 and L.wh_num_delivery_points(C.byref(cfg)) == 64
     st, ob = nv.State(), nv.Obs()
     # NULL state pointers -> WH_E_ARG, no launch
-    assert L.wh_step(C.byref(cfg), C.byref(st), 4, 0, 0, None, None, None, None, None, None, None, None, 0, None) == 10002
+    assert L.wh_step(C.byref(cfg), C.byref(st), 4, 0, 0, None, None, None, None, None, None, None, None, 0, None, None) == 10002
     assert L.wh_build_obs(C.byref(cfg), C.byref(st), 4, 0, C.byref(ob), None) == 10002
     # unsupported geometry -> WH_E_CONFIG
     bad = nv.make_config(WarehouseConfig(16, 40, (4, 8, 12, 16)))      # D = 144 > 64
@@ -125,3 +125,57 @@ def test_stats_allreduce_gloo_world2():
     for _, tot, metrics in res:
         assert tot == whole.stats.tolist()
         assert metrics["episodes"] == 64 and "avg_agent_reward_all" in metrics
+
+
+def _load_script(name):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(f"_script_{name}", os.path.join(ROOT, "scripts", f"{name}.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_rollout_cli_matches_the_reference(tmp_path):
+    """scripts/rollout.py keeps the reference's command line (rollout.py:90-113: trial_dir num_agents
+    [-i ITERATION] [-r], render off by default) and its checkpoint choice + messages (rollout.py:33-56)."""
+    ro = _load_script("rollout")
+    a = ro.parse(["/some/trial", "4", "-i", "100", "-r"])
+    assert (a.trial_dir, a.num_agents, a.iteration, a.render) == ("/some/trial", 4, 100, True)
+    a = ro.parse(["/some/trial", "2"])
+    assert a.iteration == -1 and a.render is False and a.run == "SAC" and a.num_episodes == 1
+    for n in (200, 400, 1000):
+        (tmp_path / f"checkpoint_{n}").mkdir()
+    it, path, msg = ro.pick_checkpoint(str(tmp_path), -1)
+    assert it == 1000 and path.endswith(os.path.join("checkpoint_1000", "checkpoint-1000")) and "lastest" in msg
+    it, _, msg = ro.pick_checkpoint(str(tmp_path), 400)
+    assert it == 400 and "selected checkpoint at iteration 400" in msg
+    it, _, msg = ro.pick_checkpoint(str(tmp_path), 450)
+    assert it == 400 and "doesn't exist, loading the closest one at 400" in msg
+    it, _, _ = ro.pick_checkpoint(str(tmp_path), 300)          # tie: the lower one, as min() over the sorted list does
+    assert it == 200
+
+
+def test_train_script_registers_the_vector_env_creator():
+    """scripts/train.py: same env ids as the reference (train.py:29-33); the creator yields the vectorised
+    BaseEnv adapter when asked to (needs CUDA to construct, so only the wiring is checked here) and the
+    experiment specs carry the env_config it reads; the episode metrics are the reference's (train.py:18-23)."""
+    import yaml
+    tr = _load_script("train")
+    assert set(tr.ENV_IDS) == {"WarehouseSmall-v0", "WarehouseMedium-v0", "WarehouseLarge-v0"}
+    for size in ("small", "medium", "large"):
+        spec = yaml.safe_load(open(os.path.join(ROOT, "scripts", "experiments", f"warehouse-{size}-ppo",
+                                                f"warehouse-{size}-ppo.yaml")))
+        (name, body), = spec.items()
+        assert body["run"] == "PPO" and body["env"] in tr.ENV_IDS and tr.ENV_IDS[body["env"]] == size
+        ec = body["config"]["env_config"]
+        assert ec["vector"] is True and ec["flat_obs"] is True and ec["num_envs"] >= 1
+
+    class Episode:
+        agent_rewards = {("0", "p"): 3.0, ("1", "p"): 5.0}
+        custom_metrics = {}
+    tr.episode_metrics({"episode": Episode})
+    assert Episode.custom_metrics == {"avg_agent_reward_all": [4.0], "avg_agent_reward_2": [4.0]}
+    if not torch.cuda.is_available():
+        from rllib_warehouse_b200 import _native as nv
+        with pytest.raises(nv.NativeError):                     # the creator really builds the CUDA vector env
+            tr.make_env("small", {"num_envs": 8}, vector=True)
