@@ -539,34 +539,44 @@ def extras(args, dev, peak):
         }
         del env
         torch.cuda.empty_cache()
-    # Proxy for BASELINE configs[4] (RLlib PPO rollouts; ray is not installed): sampling with an
-    # on-device torch policy (2x256 MLP, bf16, argmax) fed by the step kernel's flattened observations.
+    # BASELINE configs[4] (RLlib PPO rollouts through scripts/train.py; ray is not installed in this image):
+    # the env side of that loop THROUGH the adapter scripts/train.py registers (WarehouseVectorEnv, *Train
+    # agent counts, RLlib-flattened observations from wh_step_flat), driven by the ray-free sampler loop
+    # (rllib_warehouse_b200.RolloutSampler) with the PPO specs' policy net (fcnet 256x256, 9 logits).
     # The policy GEMMs are library code (cuBLAS through torch); the env side is this repo's kernels.
     try:
+        from rllib_warehouse_b200 import RolloutSampler, WarehouseVectorEnv, mlp_policy
+        cfg_t = VARIANTS["large"].replace(random_num_agents=True)
+        F = 9 * cfg_t.num_requests + 1
+        out4 = {}
+        # (a) strictly the BaseEnv protocol (poll / send_actions / try_reset: nested dicts of host arrays),
+        #     num_envs as in the PPO specs' env_config
+        venv = WarehouseVectorEnv(cfg_t, 256, device=dev, seed=args.seed + 3, flat_obs=True)
+        smp = RolloutSampler(venv, mlp_policy(F, 256, dev, torch.float32))
+        smp.run_base_env(3)
+        r = smp.run_base_env(30)
+        out4["base_env_protocol"] = {
+            "envs": 256, "env_steps_per_sec": r["env_steps"] / r["seconds"], "agent_steps_per_sec": r["agent_steps"] / r["seconds"],
+            "ms_per_sampler_iteration": 1e3 * r["seconds"] / 30,
+            "note": "poll/send_actions/try_reset with per-env per-agent dicts on the host: one wh_step_flat launch per "
+                    "iteration, the rest is the protocol's Python dict traffic (which RLlib's sampler pays with any env)"}
+        del venv, smp
+        # (b) the adapter's tensor API (reset_tensors / step_tensors): observations never leave HBM
         n = 65536
-        env = BatchedWarehouse(VARIANTS["large"], n, device=dev, seed=args.seed + 3, auto_reset=True)
-        env.reset()
-        F = 9 * env.R + 1
-        torch.manual_seed(0)
-        policy = torch.nn.Sequential(torch.nn.Linear(F, 256), torch.nn.ReLU(), torch.nn.Linear(256, 256),
-                                     torch.nn.ReLU(), torch.nn.Linear(256, 9)).to(dev, torch.bfloat16)
-        flat = [env.build_obs_flat(1)]
-
-        def sample(i):
-            with torch.no_grad():
-                logits = policy(flat[0].view(-1, F).to(torch.bfloat16))
-                actions = logits.argmax(dim=-1).view(n, env.R).to(torch.int32)
-            flat[0], _, _ = env.step_flat(actions)
-
-        ms_pol = _time_steps(sample, 50, 5)
-        res["configs4_proxy_torch_policy_rollout"] = {
-            "ms": ms_pol, "agent_steps_per_sec": n * 16 / (ms_pol * 1e-3), "envs": n,
-            "note": "large, 65 536 envs; per step: wh_step_flat + bf16 MLP 145-256-256-9 over 1 048 576 agent rows + argmax",
-        }
-        del env, policy, flat
+        venv = WarehouseVectorEnv(cfg_t, n, device=dev, seed=args.seed + 4, flat_obs=True, auto_reset=True)
+        smp = RolloutSampler(venv, mlp_policy(F, 256, dev, torch.bfloat16))
+        smp.run_tensor(5)
+        r = smp.run_tensor(50)
+        out4["tensor_api"] = {
+            "envs": n, "env_steps_per_sec": r["env_steps"] / r["seconds"], "agent_rows_per_sec": r["agent_steps"] / r["seconds"],
+            "ms_per_sampler_iteration": 1e3 * r["seconds"] / 50,
+            "note": "per iteration: wh_step_flat (65 536 Large envs, 1..16 agents each) + bf16 MLP 145-256-256-9 over "
+                    "1 048 576 agent rows + argmax; episode bookkeeping on device"}
+        res["configs4_sampler_through_vector_env_adapter"] = out4
+        del venv, smp
         torch.cuda.empty_cache()
     except Exception as e:  # noqa: BLE001
-        res["configs4_proxy_torch_policy_rollout"] = {"error": repr(e)}
+        res["configs4_sampler_through_vector_env_adapter"] = {"error": repr(e)}
     # BASELINE configs[1] shape (Small, 4 096 envs): launch-bound eagerly, so also as a CUDA graph
     from rllib_warehouse_b200 import StepGraph
     env = BatchedWarehouse(VARIANTS["small"], 4096, device=dev, seed=args.seed + 2, auto_reset=True)
