@@ -19,9 +19,12 @@ OBS_KEYS = nv.OBS_KEYS
 def _dev_tensor(x, dtype, device, shape=None):
     if x is None:
         return None
-    if (isinstance(x, torch.Tensor) and x.dtype == dtype and x.device == device and x.is_contiguous()
-            and (shape is None or tuple(x.shape) == tuple(shape))):
-        return x                              # the per-step fast path: already what the kernel needs
+    if (isinstance(x, torch.Tensor) and x.dtype == dtype and x.is_contiguous()
+            and (shape is None or tuple(x.shape) == tuple(shape))
+            and (x.device == device or (x.device.type == "cpu" and x.is_pinned()))):
+        # the per-step fast path: already what the kernel needs — a tensor on the device, or page-locked
+        # host memory, which the kernels address directly (unified addressing; see Arena(mapped=True))
+        return x
     if not isinstance(x, torch.Tensor):
         x = torch.from_numpy(np.ascontiguousarray(x))
     x = x.to(device=device, dtype=dtype).contiguous()
@@ -37,22 +40,36 @@ def _ptr(t):
 class Arena:
     """Several tensors as views into ONE device allocation (every view 256-byte aligned) with a pinned
     host twin of the same layout, so that a host-driven caller moves all of them with a single copy
-    (the per-env dict API of `core.Warehouse` / `solvers.WarehouseRandomGreedySolver`: one D2H per
-    step instead of one per observation key)."""
+    (`WarehouseVectorEnv`: one D2H per step instead of one per observation key).
 
-    def __init__(self, specs, device):
+    mapped=True (the one-env dict API of `core.Warehouse` / `solvers.WarehouseRandomGreedySolver`): there is
+    no device copy at all — the views ARE the page-locked host buffer, and the kernels read / write it
+    directly over PCIe (unified addressing: a cudaHostAlloc'ed pointer is valid on the device). For a
+    handful of kilobytes per step that replaces two cudaMemcpyAsync round trips by nothing: a step is one
+    launch + one stream synchronisation."""
+
+    def __init__(self, specs, device, mapped=False):
         self.offsets, total = {}, 0
+        self.mapped, self.device = bool(mapped), torch.device(device)
         for name, shape, dtype in specs:
             total = (total + 255) // 256 * 256
             nbytes = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
             self.offsets[name] = (total, nbytes, shape, dtype)
             total += nbytes
-        self.dev = torch.zeros(max(total, 256), dtype=torch.uint8, device=device)
-        self.views = {k: self.dev[o:o + n].view(dt).view(sh) for k, (o, n, sh, dt) in self.offsets.items()}
         self._host = None
         self.host_views = None
+        if self.mapped:
+            self.dev = torch.zeros(max(total, 256), dtype=torch.uint8).pin_memory()
+        else:
+            self.dev = torch.zeros(max(total, 256), dtype=torch.uint8, device=device)
+        self.views = {k: self.dev[o:o + n].view(dt).view(sh) for k, (o, n, sh, dt) in self.offsets.items()}
+        if self.mapped:
+            self.host()
 
     def host(self):
+        if self._host is None and self.mapped:
+            self._host = self.dev
+            self.host_views = {k: v.numpy() for k, v in self.views.items()}
         if self._host is None:
             self._host = torch.zeros(self.dev.shape, dtype=torch.uint8).pin_memory()
             self.host_views = {k: self._host[o:o + n].view(dt).view(sh).numpy()
@@ -61,6 +78,9 @@ class Arena:
 
     def to_host(self):
         """device -> pinned host, one copy; returns numpy views (valid until the next call)."""
+        if self.mapped:                       # the kernels wrote the host buffer themselves: wait for them
+            torch.cuda.current_stream(self.device).synchronize()
+            return self.host_views
         h = self.host()
         h.copy_(self.dev, non_blocking=True)
         torch.cuda.current_stream(self.dev.device).synchronize()
@@ -68,7 +88,8 @@ class Arena:
 
     def to_device(self):
         """pinned host (filled through `host_views`) -> device, one asynchronous copy."""
-        self.dev.copy_(self.host(), non_blocking=True)
+        if not self.mapped:
+            self.dev.copy_(self.host(), non_blocking=True)
         return self.views
 
 
@@ -100,10 +121,12 @@ class BatchedWarehouse:
     `reset(num_agents=...)` (replay) or drawn on device when `config.random_num_agents` (*Train).
     env_id0: global id of env 0 on this shard; the RNG is keyed by the GLOBAL env id, so results
     do not depend on how envs are split over GPUs.
+    mapped_io: observations / rewards / dones live in page-locked HOST memory that the kernels write
+    directly (for the one-env dict API: no device->host copy per step); `obs` etc. are then CPU tensors.
     """
 
     def __init__(self, config: WarehouseConfig, num_envs: int, num_agents=None, device="cuda:0",
-                 seed: int = 0, env_id0: int = 0, auto_reset: bool = False):
+                 seed: int = 0, env_id0: int = 0, auto_reset: bool = False, mapped_io: bool = False):
         if not torch.cuda.is_available():
             raise nv.NativeError("BatchedWarehouse needs a CUDA device: there is no CPU fallback")
         self.lib = nv.lib()
@@ -137,7 +160,7 @@ class BatchedWarehouse:
             ("self_availability", (N, R, 1), i8), ("self_delivery_target", (N, R, 2), i32),
             ("other_positions", (N, R, R - 1, 2), i32), ("other_availabilities", (N, R, R - 1), i8),
             ("other_delivery_targets", (N, R, R - 1, 2), i32), ("requests", (N, R, R, 4), i32),
-            ("rewards", (N, R), torch.float32), ("dones", (N,), torch.uint8)], dev)
+            ("rewards", (N, R), torch.float32), ("dones", (N,), torch.uint8)], dev, mapped=mapped_io)
         self.obs = {k: self._out.views[k] for k in OBS_KEYS}
         self.rewards = self._out.views["rewards"]
         self.dones = self._out.views["dones"]

@@ -52,12 +52,12 @@ class Warehouse(MultiAgentEnv):
         # only supplies the 64-bit key of the device-side counter-based generator.
         if seed is None:
             seed = int(np.random.randint(0, 2**31 - 1)) | (int(np.random.randint(0, 2**31 - 1)) << 31)
+        # One env, driven from the host through dicts: inputs and outputs live in page-locked host memory that
+        # the kernels address directly — a step is one launch + one stream synchronisation, no copies.
         self._batched = BatchedWarehouse(self._config, 1, num_agents=num_agents,
-                                         device=device or _DEFAULT_DEVICE, seed=seed)
-        # actions + dict order travel in one pinned buffer / one H2D copy per step
+                                         device=device or _DEFAULT_DEVICE, seed=seed, mapped_io=True)
         self._in = Arena([("actions", (1, num_requests), torch.int32), ("order", (1, num_requests), torch.int32)],
-                         self._batched.device)
-        self._in.host()
+                         self._batched.device, mapped=True)
         self._num_agents = num_agents
         self._num_requests = num_requests
         # core.py:111-118
@@ -72,7 +72,7 @@ class Warehouse(MultiAgentEnv):
 
     # ------------------------------------------------------------------------------------------
     def _obs_dicts(self, host=None) -> Dict[str, Dict[str, np.ndarray]]:
-        # one device->host copy for all keys; the per-agent arrays are fresh copies, as in the
+        # the kernel wrote the page-locked host buffer; the per-agent arrays are fresh copies, as in the
         # reference (callers may keep them across steps)
         host = self._batched.outputs_to_host() if host is None else host
         A = self.num_agents

@@ -74,13 +74,19 @@ struct StageMem {
     }
 };
 
-// Per-episode event counters (touched only on events) and, when an episode ends, the statistics
-// vector that mirrors scripts/train.py:18-23. `owner` = the one lane of a live env that does it.
+// Per-episode event counters and, when an episode ends, the statistics vector that mirrors
+// scripts/train.py:18-23. `owner` = the one lane of a live env that does it. The counters (`a`, 16 bytes per
+// env) are loaded by the caller together with the rest of the state at kernel entry — loading them here, on
+// demand, put a full DRAM round trip on the critical path of nearly every warp (some env of a warp has an
+// event in most steps): 6-8 % of all warp stall samples (profiles/r02_hotspots_*.txt) — and are stored back
+// only when this step changed them (`dirty`). Measured: Medium +1 %, Medium-65536 greedy +3.5 %, Large +0.3 %;
+// Small -1.8 % (its 16 extra bytes per env are 2 % more traffic), so Small (EARLY = false) still loads on demand.
+template <bool EARLY>
 __device__ __forceinline__ void account_episode(const KParams &P, bool owner, env_t e, const StepOut &so,
-                                                const EnvRegs &s, bool done, bool auto_reset) {
+                                                const EnvRegs &s, bool done, bool auto_reset, int4 &a, bool &dirty) {
     const bool flush = s.time == P.episode;
     if (owner && ((so.npick | so.ndeliv | so.nexp) != 0 || flush || (auto_reset && done))) {
-        int4 a = reinterpret_cast<int4 *>(P.acc)[e];
+        if (!EARLY) a = reinterpret_cast<const int4 *>(P.acc)[e];
         a.x += so.npick; a.y += so.ndeliv; a.z += so.nexp;
         if (P.stats && flush) {                                                // train.py:18-23
             const unsigned long long ret = (unsigned long long)(a.x + a.y);
@@ -93,7 +99,7 @@ __device__ __forceinline__ void account_episode(const KParams &P, bool owner, en
             atomicAdd(P.stats + 9 + 2 * (s.A - 1), ret);
         }
         if (auto_reset && done) a = make_int4(0, 0, 0, 0);
-        reinterpret_cast<int4 *>(P.acc)[e] = a;
+        dirty = true;
     }
 }
 
@@ -116,6 +122,10 @@ __global__ void __launch_bounds__(BLOCK, (RC == 16 ? WH_MIN_BLOCKS_LARGE : RC ==
     EnvRegs s;
     asm volatile("griddepcontrol.wait;" ::: "memory");
     load_env(P, g, e, R, (RC ? 4 * GC : P.P), s);
+    int4 acc4 = make_int4(0, 0, 0, 0);
+    bool acc_dirty = false;
+    constexpr bool EARLY_ACC = RC != 4;
+    if (EARLY_ACC && g.gl == 0) acc4 = reinterpret_cast<const int4 *>(P.acc)[e];   // with the rest of the state, see account_episode
 
     // envs masked out of this step (BaseEnv.send_actions for a subset of the envs) compute along but write nothing
     const bool live = t.live && (PLAIN || !P.env_mask || P.env_mask[e] != 0);
@@ -143,7 +153,8 @@ __global__ void __launch_bounds__(BLOCK, (RC == 16 ? WH_MIN_BLOCKS_LARGE : RC ==
         if (g.gl == 0) P.dones[e] = done ? 1 : 0;
     }
     const bool auto_reset = (P.flags & WH_FLAG_AUTO_RESET) != 0;
-    account_episode(P, g.gl == 0 && live, e, so, s, done, auto_reset);
+    account_episode<EARLY_ACC>(P, g.gl == 0 && live, e, so, s, done, auto_reset, acc4, acc_dirty);
+    if (acc_dirty) reinterpret_cast<int4 *>(P.acc)[e] = acc4;
     int flavour = WH_OBS_STEP;
     bool meta = false;
     if (auto_reset && __any_sync(FULL, done)) {
@@ -177,6 +188,9 @@ __global__ void __launch_bounds__(BLOCK, (RC == 16 ? 4 : WH_MIN_BLOCKS)) k_rollo
     const bool auto_reset = (P.flags & WH_FLAG_AUTO_RESET) != 0;
     float ret = 0.0f;
     bool done = false;
+    int4 acc4 = make_int4(0, 0, 0, 0);
+    bool acc_dirty = false;
+    if (g.gl == 0) acc4 = reinterpret_cast<const int4 *>(P.acc)[e];
     for (int it = 0; it < P.n_steps; ++it) {
         const int act = greedy_from_state<GC, RC>(P, g, R, env_id, s);
         s.time += 1;                                                           // core.py:267
@@ -184,11 +198,12 @@ __global__ void __launch_bounds__(BLOCK, (RC == 16 ? 4 : WH_MIN_BLOCKS)) k_rollo
         const StepOut so = do_world(P, g, e, R, env_id, s, false);
         ret += so.reward;
         done = s.time >= P.episode;                                            // core.py:438
-        account_episode(P, g.gl == 0 && t.live, e, so, s, done, auto_reset);
+        account_episode<true>(P, g.gl == 0 && t.live, e, so, s, done, auto_reset, acc4, acc_dirty);
         if (auto_reset && __any_sync(FULL, done)) do_reset(P, g, e, R, env_id, s, false, done && t.live);
     }
     if (t.live) {
         store_env(P, g, e, R, (RC ? 4 * GC : P.P), s, true);
+        if (acc_dirty) reinterpret_cast<int4 *>(P.acc)[e] = acc4;
         if (g.gl < R) P.rewards[e * R + g.gl] = ret;
         if (g.gl == 0) P.dones[e] = done ? 1 : 0;
     }
@@ -220,6 +235,9 @@ __global__ void __launch_bounds__(BLOCK, (RC == 16 ? WH_MIN_BLOCKS_LARGE : RC ==
     const size_t NR = (size_t)P.N * R, N = (size_t)P.N;
     float ret = 0.0f;
     bool done = false;
+    int4 acc4 = make_int4(0, 0, 0, 0);
+    bool acc_dirty = false;
+    if (g.gl == 0) acc4 = reinterpret_cast<const int4 *>(P.acc)[e];
     for (int it = 0; it < P.n_steps; ++it) {
         int act = -1;
         if (GREEDY) act = greedy_from_state<GC, RC>(P, g, R, env_id, s);
@@ -234,7 +252,7 @@ __global__ void __launch_bounds__(BLOCK, (RC == 16 ? WH_MIN_BLOCKS_LARGE : RC ==
         } else {
             ret += so.reward;
         }
-        account_episode(P, g.gl == 0 && t.live, e, so, s, done, auto_reset);
+        account_episode<true>(P, g.gl == 0 && t.live, e, so, s, done, auto_reset, acc4, acc_dirty);
         unsigned long long active = so.active;
         int flavour = WH_OBS_STEP;
         if (auto_reset && __any_sync(FULL, done)) {
@@ -258,6 +276,7 @@ __global__ void __launch_bounds__(BLOCK, (RC == 16 ? WH_MIN_BLOCKS_LARGE : RC ==
     }
     if (t.live) {
         store_env(P, g, e, R, (RC ? 4 * GC : P.P), s, true);
+        if (acc_dirty) reinterpret_cast<int4 *>(P.acc)[e] = acc4;
         if (!per_step) {
             if (g.gl < R) P.rewards[e * R + g.gl] = ret;
             if (g.gl == 0) P.dones[e] = done ? 1 : 0;
@@ -509,7 +528,9 @@ static void launch_kind(Kind kind, const KParams &K, cudaStream_t s) {
     case K_MULTI:
     case K_GMULTI: {
         // launch-sized batches: with fewer warps than the GPU has schedulers, spread them over the SMs
-        // (2-warp blocks) instead of packing 8 per block
+        // (2-warp blocks) instead of packing 8 per block. (Giving each warp fewer environments to put more
+        // warps in flight was measured and is worse: 4 096 Small envs 2.7 -> 5.5 us per step — a step is one
+        // long dependent chain per warp, so extra warps only add instructions.)
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
         const unsigned threads = warps >= (long long)sms * 16 ? BLOCK : 64;
@@ -790,6 +811,7 @@ struct wh_env {
     int64_t N, env_id0;
     uint64_t seed;
     int device, n_chunks, R, P;
+    int direct;      // 0 = copy pipeline; 1 = the kernel reads actions from / writes rewards + dones to the host buffers; 2 = outputs only
     wh_state st;
     wh_obs obs;
     int32_t *d_actions;
@@ -854,7 +876,11 @@ int wh_env_create(const wh_config *cfg, int64_t n_envs, int device, int64_t env_
     memset(E, 0, sizeof(*E));
     E->cfg = *cfg; E->N = n_envs; E->env_id0 = env_id0; E->seed = seed; E->device = device;
     E->R = K.R; E->P = K.P;
-    if (n_chunks < 1) n_chunks = 1;
+    // n_chunks <= 0 selects the direct (zero-copy) modes, see wh_env_step_host: 0 = inputs and outputs,
+    // -k = outputs only, inputs through a k-chunk copy pipeline
+    E->direct = n_chunks == 0 ? 1 : (n_chunks < 0 ? 2 : 0);
+    if (n_chunks == 0) n_chunks = 1;
+    if (n_chunks < 0) n_chunks = -n_chunks;
     if (n_chunks > 64) n_chunks = 64;
     E->n_chunks = n_chunks;
     if (int rc = env_alloc(E, K, n_chunks)) {   // a failed allocation leaves nothing behind
@@ -893,10 +919,51 @@ int wh_env_reset(wh_env *E) {
     return 0;
 }
 
+// Is `p` page-locked host memory this device can address (cudaHostAlloc / cudaHostRegister / torch pin_memory)?
+static bool device_can_address(const void *p, void **dev_ptr) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (a.type != cudaMemoryTypeHost || !a.devicePointer) return false;
+    *dev_ptr = a.devicePointer;
+    return true;
+}
+
 static int env_step_issue(wh_env *E, const int32_t *actions, float *rewards, uint8_t *dones,
                          const wh_obs *obs_host, bool greedy, bool compact) {
     CK(cudaSetDevice(E->device));
     const int64_t R = E->R;
+    // Direct modes: the step kernel itself moves the step's I/O over PCIe — it writes rewards and dones
+    // straight into the caller's page-locked buffers (and, mode 1, reads the actions from them), so there is
+    // no separate copy to wait for before / after the kernel. Falls back to the copy pipeline when a buffer
+    // is not page-locked.
+    void *d_act = nullptr, *d_rew = nullptr, *d_done = nullptr;
+    const bool out_direct = E->direct && device_can_address(rewards, &d_rew) && device_can_address(dones, &d_done);
+    const bool in_direct = out_direct && E->direct == 1 && (greedy || device_can_address(actions, &d_act));
+    if (out_direct && in_direct) {
+        cudaStream_t s = E->streams[0];
+        int rc;
+        const int fl = WH_FLAG_AUTO_RESET | (compact ? WH_FLAG_COMPACT_IO : 0);
+        if (greedy)
+            rc = wh_greedy_step(&E->cfg, &E->st, E->N, E->env_id0, E->seed, E->seed ^ 0x5EEDull, 0, nullptr,
+                                (float *)d_rew, (uint8_t *)d_done, E->d_stats, &E->obs, fl, s);
+        else
+            rc = wh_step(&E->cfg, &E->st, E->N, E->env_id0, E->seed, (const int32_t *)d_act, nullptr, nullptr, nullptr,
+                         (float *)d_rew, (uint8_t *)d_done, E->d_stats, &E->obs, fl, nullptr, s);
+        E->launches += 1;
+        if (rc) return rc;
+        if (obs_host) {
+            const wh_obs &ob = E->obs; const wh_obs &oh = *obs_host; const int64_t n = E->N;
+            CK(cudaMemcpyAsync(oh.num_agents, ob.num_agents, n * R * 4, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(oh.self_position, ob.self_position, n * R * 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(oh.self_availability, ob.self_availability, n * R, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(oh.self_delivery_target, ob.self_delivery_target, n * R * 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(oh.other_positions, ob.other_positions, n * R * (R - 1) * 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(oh.other_availabilities, ob.other_availabilities, n * R * (R - 1), cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(oh.other_delivery_targets, ob.other_delivery_targets, n * R * (R - 1) * 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(oh.requests, ob.requests, n * R * R * 16, cudaMemcpyDeviceToHost, s));
+        }
+        return 0;
+    }
     for (int c = 0; c < E->n_chunks; ++c) {
         const int64_t e0 = E->N * c / E->n_chunks, e1 = E->N * (c + 1) / E->n_chunks, n = e1 - e0;
         if (n <= 0) continue;
@@ -918,7 +985,8 @@ static int env_step_issue(wh_env *E, const int32_t *actions, float *rewards, uin
             } else {
                 CK(cudaMemcpyAsync(E->d_actions + e0 * R, actions + e0 * R, n * R * 4, cudaMemcpyHostToDevice, s));
                 rc = wh_step(&E->cfg, &st, n, E->env_id0 + e0, E->seed, E->d_actions + e0 * R, nullptr, nullptr,
-                             nullptr, E->d_rewards + e0 * R, E->d_dones + e0, E->d_stats, &ob,
+                             nullptr, out_direct ? (float *)d_rew + e0 * R : E->d_rewards + e0 * R,
+                             out_direct ? (uint8_t *)d_done + e0 : E->d_dones + e0, E->d_stats, &ob,
                              WH_FLAG_AUTO_RESET | WH_FLAG_NO_PDL, nullptr, s);
             }
         }
@@ -927,9 +995,10 @@ static int env_step_issue(wh_env *E, const int32_t *actions, float *rewards, uin
         if (compact)
             CK(cudaMemcpyAsync(reinterpret_cast<uint8_t *>(rewards) + e0 * R, reinterpret_cast<uint8_t *>(E->d_rewards) + e0 * R,
                                n * R, cudaMemcpyDeviceToHost, s));
-        else
+        else if (!out_direct || greedy)
             CK(cudaMemcpyAsync(rewards + e0 * R, E->d_rewards + e0 * R, n * R * 4, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(dones + e0, E->d_dones + e0, n, cudaMemcpyDeviceToHost, s));
+        if (compact || !out_direct || greedy)
+            CK(cudaMemcpyAsync(dones + e0, E->d_dones + e0, n, cudaMemcpyDeviceToHost, s));
         if (obs_host) {
             const wh_obs oh = offset_obs(*obs_host, e0, R);
             CK(cudaMemcpyAsync(oh.num_agents, ob.num_agents, n * R * 4, cudaMemcpyDeviceToHost, s));

@@ -79,7 +79,7 @@ struct KParams {
     long long N, env_id0;
     unsigned long long seed, solver_seed, rand_thr;
     int flags, flavour;
-    int n_steps;        // k_rollout: steps per launch
+    int n_steps;        // k_rollout / k_multi: steps per launch
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -836,6 +836,32 @@ __device__ __forceinline__ const uint8_t *flat_map() {
     else return d_flat_map16.m;
 }
 
+// The same map composed with the warp layout: entry k (k-th float of the warp's contiguous output range of
+// 32/G environments) = word offset of its source inside the warp's staging area (env * VS + swizzled table
+// address). One 64-bit load yields the four sources of a 128-bit store; no per-element index arithmetic.
+template <int RC>
+struct FlatWarpMap {
+    using M = FlatMap<RC>;
+    static constexpr int EPW = 32 / (RC ? RC : 1);
+    static constexpr int TOT = EPW * M::RF;
+    alignas(16) uint16_t w[TOT + 8];
+    constexpr FlatWarpMap() : w{} {
+        for (int env = 0; env < EPW; ++env)
+            for (int a = 0; a < M::R; ++a)
+                for (int f = 0; f < M::F; ++f)
+                    w[env * M::RF + a * M::F + f] = (uint16_t)(env * M::VS + M::swz(M::src(a, f)));
+    }
+};
+__device__ const FlatWarpMap<4> d_flat_wmap4{};
+__device__ const FlatWarpMap<9> d_flat_wmap9{};
+__device__ const FlatWarpMap<16> d_flat_wmap16{};
+template <int RC>
+__device__ __forceinline__ const uint16_t *flat_warp_map() {
+    if constexpr (RC == 4) return d_flat_wmap4.w;
+    else if constexpr (RC == 9) return d_flat_wmap9.w;
+    else return d_flat_wmap16.w;
+}
+
 template <int RC>
 struct FlatStage {
     static constexpr int BYTES = RC ? FlatMap<RC>::VS * 4 : 16;            // one environment's value table
@@ -907,6 +933,51 @@ __device__ __forceinline__ void build_obs_flat(const KParams &P, const Group<GC>
         static_assert(M::RF % 2 == 0, "pairs never straddle environments");
         static_assert(EPW <= 3 || ((EPW * M::RF - 1) * ((65536 + M::RF - 1) / M::RF)) >> 16 == EPW - 1, "reciprocal division range");
         constexpr int ITERS = (TOT / 4 + 31) / 32;
+        // Fast path (always, unless an env mask punches holes): the written environments are a prefix of the
+        // warp's range, so liveness is one compare and the composed warp map gives the sources directly.
+        int live_envs = 0;
+        bool prefix = true;
+#pragma unroll
+        for (int t = 0; t < EPW; ++t) {
+            const bool l = env_live(t);
+            prefix = prefix && !(l && live_envs != t);               // a live env after a dead one: not a prefix
+            live_envs += l ? 1 : 0;
+        }
+        // (Large keeps the per-element map: its 9.3 KB composed table measured 3 % slower, HBM-bound either way)
+        if (prefix && RC != 16) {
+            const uint16_t *wm = flat_warp_map<RC>();
+            const int limit = live_envs * M::RF;
+            const int nbl = limit > head ? (limit - head) >> 2 : 0;
+#pragma unroll 4
+            for (int it = 0; it < ITERS; ++it) {
+                const int i = g.lane + 32 * it;
+                if (i < nbl) {
+                    const int k = head + 4 * i;
+                    uint32_t lo, hi;
+                    if constexpr (M::RF % 4 == 0) {
+                        const uint2 v = __ldg(reinterpret_cast<const uint2 *>(wm + k));
+                        lo = v.x; hi = v.y;
+                    } else {
+                        lo = __ldg(reinterpret_cast<const uint32_t *>(wm + k));
+                        hi = __ldg(reinterpret_cast<const uint32_t *>(wm + k + 2));
+                    }
+                    WH_ST(reinterpret_cast<float4 *>(wout + k),
+                          make_float4(wstage[lo & 0xFFFFu], wstage[lo >> 16], wstage[hi & 0xFFFFu], wstage[hi >> 16]));
+                }
+            }
+            if constexpr (M::RF % 4 != 0) {                                  // 8-byte head / tail of a misaligned range
+                if (g.lane == 0 && head == 2 && limit >= 2) {
+                    const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(wm));
+                    WH_ST(reinterpret_cast<float2 *>(wout), make_float2(wstage[v & 0xFFFFu], wstage[v >> 16]));
+                }
+                const int tail = head + 4 * nbl;
+                if (g.lane == 1 && limit > 0 && tail < limit) {
+                    const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(wm + tail));
+                    WH_ST(reinterpret_cast<float2 *>(wout + tail), make_float2(wstage[v & 0xFFFFu], wstage[v >> 16]));
+                }
+            }
+            return;
+        }
         const int nb = (TOT - head) >> 2;                                    // whole float4 in the range
 #pragma unroll 4
         for (int it = 0; it < ITERS; ++it) {

@@ -51,15 +51,15 @@ class WarehouseRandomGreedySolver(WarehouseSolver):
         cfg = WarehouseConfig(num_requests, dim, tuple(4 * (i + 1) for i in range(L)), 200, 200, num_requests)
         self._env = BatchedWarehouse(cfg, 1, num_agents=num_agents, device=device)
         R = num_requests
-        # the four keys the solver reads (solvers.py:33-39) + the replayed eps-random branch, packed
-        # in one pinned buffer: one H2D copy, one wh_greedy launch, one D2H copy per call
+        # the four keys the solver reads (solvers.py:33-39) + the replayed eps-random branch, packed in one
+        # page-locked buffer that wh_greedy reads directly; the actions come back the same way: one launch
+        # and one stream synchronisation per call, no copies
         self._in = Arena([("self_position", (1, R, 2), torch.int32), ("self_availability", (1, R, 1), torch.int8),
                           ("self_delivery_target", (1, R, 2), torch.int32), ("requests", (1, R, R, 4), torch.int32),
                           ("is_random", (1, R), torch.uint8), ("random_actions", (1, R), torch.int32)],
-                         self._env.device)
-        self._in.host()
+                         self._env.device, mapped=True)
         self._ob = nv.Obs(**{k: (self._in.views[k].data_ptr() if k in self._in.views else None) for k in OBS_KEYS})
-        self._out = Arena([("actions", (1, R), torch.int32)], self._env.device)
+        self._out = Arena([("actions", (1, R), torch.int32)], self._env.device, mapped=True)
 
     def compute_action(self, observations: Dict[str, Dict[str, np.ndarray]]) -> Dict[str, np.ndarray]:
         A = self._num_agents

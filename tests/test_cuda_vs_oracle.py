@@ -236,9 +236,10 @@ def test_flat_observations(size):
         assert np.array_equal(gpu.build_obs_flat().cpu().numpy(), oracle_flat(cpu))
 
 
-@pytest.mark.parametrize("compact", [False, True])
-def test_host_buffer_layer(compact):
-    """Layer 2 of the C ABI (wh_env_*: host buffers, chunked copy/compute pipeline, both wire
+@pytest.mark.parametrize("compact,chunks", [(False, 3), (True, 3), (False, 0), (True, 0), (False, -3)])
+def test_host_buffer_layer(compact, chunks):
+    """Layer 2 of the C ABI (wh_env_*: host buffers; chunked copy/compute pipeline, the direct mode in which
+    the kernel reads / writes the page-locked host buffers itself, and the outputs-direct mode; both wire
     formats) gives exactly what the device-pointer layer gives on the same seed and actions."""
     import ctypes as C
     from rllib_warehouse_b200 import MEDIUM, BatchedWarehouse
@@ -247,7 +248,7 @@ def test_host_buffer_layer(compact):
     n, R, seed, id0 = 5003, 9, 321, 1000
     h = C.c_void_p()
     cfg = nv.make_config(MEDIUM)
-    nv.check(L.wh_env_create(C.byref(cfg), n, 0, id0, seed, 3, C.byref(h)), "create")
+    nv.check(L.wh_env_create(C.byref(cfg), n, 0, id0, seed, chunks, C.byref(h)), "create")
     nv.check(L.wh_env_reset(h), "reset")
     twin = BatchedWarehouse(MEDIUM, n, seed=seed, env_id0=id0, auto_reset=True)
     twin.reset()
@@ -275,7 +276,7 @@ def test_host_buffer_layer(compact):
     assert list(stats) == twin.stats.cpu().tolist() and stats[0] == n
     st = nv.State()
     nv.check(L.wh_env_state_ptrs(h, C.byref(st)), "state ptrs")
-    assert st.agent_pos and L.wh_env_launch_count(h) == 1 + 205 * 3
+    assert st.agent_pos and L.wh_env_launch_count(h) == 1 + 205 * (abs(chunks) if chunks else 1)
     L.wh_env_destroy(h)
 
 

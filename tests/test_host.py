@@ -179,3 +179,24 @@ def test_train_script_registers_the_vector_env_creator():
         from rllib_warehouse_b200 import _native as nv
         with pytest.raises(nv.NativeError):                     # the creator really builds the CUDA vector env
             tr.make_env("small", {"num_envs": 8}, vector=True)
+
+
+def test_reference_copy_is_verbatim_and_tamper_evident(tmp_path, monkeypatch):
+    """oracle/_ref (oracle/make_ref.py) is a verbatim copy of the reference's hot-path files: the manifest
+    hashes match the mounted reference where it is available, and any edit of a copied file is detected."""
+    import shutil
+    from oracle import make_ref
+    if not make_ref.available() and make_ref.make() is None:
+        pytest.skip("neither /root/reference nor oracle/_ref on this box")
+    assert make_ref.verify()
+    ref = os.environ.get("WH_REFERENCE", "/root/reference")
+    if os.path.isdir(os.path.join(ref, "warehouse")):
+        for rel in make_ref.FILES:
+            assert open(os.path.join(ref, rel), "rb").read() == open(os.path.join(make_ref.OUT, rel), "rb").read(), rel
+    clone = tmp_path / "_ref"
+    shutil.copytree(make_ref.OUT, clone)
+    monkeypatch.setattr(make_ref, "OUT", str(clone))
+    assert make_ref.verify()
+    with open(clone / "warehouse" / "core.py", "a") as f:
+        f.write("\n# edited\n")
+    assert not make_ref.verify()
