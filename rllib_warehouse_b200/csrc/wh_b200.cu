@@ -520,7 +520,10 @@ static void launch_kind(Kind kind, const KParams &K, cudaStream_t s) {
         if (plain) launch_step(k_step<GC, RC, true, false, RC != 0>, grid, dyn, s, K);
         else launch_step(k_step<GC, RC, true, false>, grid, dyn, s, K);
         break;
-    case K_STEP_FLAT: launch_step(k_step<GC, RC, false, true>, grid, 0, s, K); break;
+    case K_STEP_FLAT:
+        if (plain) launch_step(k_step<GC, RC, false, true, RC != 0>, grid, 0, s, K);
+        else launch_step(k_step<GC, RC, false, true>, grid, 0, s, K);
+        break;
     case K_RESET: k_reset<GC, RC><<<grid, BLOCK, 0, s>>>(K); break;
     case K_OBS: k_obs<GC, RC><<<grid, BLOCK, 0, s>>>(K); break;
     case K_OBS_FLAT: k_obs_flat<GC, RC><<<grid, BLOCK, 0, s>>>(K); break;
