@@ -55,8 +55,8 @@ def parse():
     ap.add_argument("--policy", default="random", choices=["random", "greedy", "greedy_fused"])
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--e2e-chunks", type=int, default=None,
-                    help="wh_env_create n_chunks for every e2e leg (k > 0: k-chunk copy pipeline, 0: direct, -k: outputs "
-                         "direct); default: the measured best per wire format (0 for int32/float32, 8 for int8/uint8)")
+                    help="wh_env_create n_chunks for every e2e leg (k > 0: k-chunk copy pipeline, 0: direct); "
+                         "default: direct for e2e / e2e_alt, 8-chunk pipeline for e2e_host_obs")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--cpu-envs", type=int, default=8192, help="sample size (envs) of the CPU legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -453,10 +453,9 @@ def run_b200(args):
                 "h2d_bytes_per_step": n_local * R * host_actions[0].element_size(),
                 "d2h_bytes_per_step": n_local * R * host_rewards.element_size() + n_local + obs_bytes,
                 "steps": steps, "ms_per_step": 1e3 * dt / steps, "chunks": chunks,
-                "transport": ("direct: one kernel over all envs reads the actions from and writes rewards + dones to the "
-                              "page-locked host buffers itself" if chunks == 0 else
-                              f"{abs(chunks)}-chunk pipeline of cudaMemcpyAsync H2D -> kernel"
-                              + (" writing the host buffers directly" if chunks < 0 else " -> cudaMemcpyAsync D2H")),
+                "transport": ("direct: one kernel over all envs reads the actions from and writes the rewards to the "
+                              "page-locked host buffers itself (dones: one small D2H copy)" if chunks <= 0 else
+                              f"{chunks}-chunk pipeline of cudaMemcpyAsync H2D -> kernel -> cudaMemcpyAsync D2H"),
                 "api": api + "; C ABI, pinned host buffers",
                 "reward_checksum": float(host_rewards.sum()), "gpu_launches": launches,
             }
@@ -466,11 +465,11 @@ def run_b200(args):
             L.wh_env_destroy(h)
             return res
 
-        # transport per leg = the one measured faster for that wire format (profiles/README.md, e2e sweep):
-        # direct mode for 4-byte elements, the 8-chunk copy pipeline for 1-byte elements; --e2e-chunks overrides
+        # transport: the direct mode measured faster than the copy pipeline for both wire formats
+        # (profiles/README.md, e2e sweep); the pipeline number is kept beside it; --e2e-chunks overrides
         ch = args.e2e_chunks
         out["e2e"] = run_e2e("ref_dtypes", 0 if ch is None else ch, args.e2e_steps)
-        out["e2e_alt"] = run_e2e("compact", 8 if ch is None else ch, args.e2e_steps)
+        out["e2e_alt"] = run_e2e("compact", 0 if ch is None else ch, args.e2e_steps)
         if world == 1:
             try:
                 out["e2e_copy_pipeline"] = run_e2e("ref_dtypes", 8, args.e2e_steps)

@@ -212,11 +212,11 @@ typedef struct wh_env wh_env;
  * resident in HBM (wh_env_obs_ptrs); wh_env_step_host copies them out only when given obs_host.
  * n_chunks selects how a step's host I/O crosses PCIe:
  *   k > 0   copy pipeline: k chunks of [cudaMemcpyAsync H2D actions -> kernel -> cudaMemcpyAsync D2H];
- *   0       direct: ONE kernel over all envs reads the actions from, and writes rewards + dones to, the
- *           caller's page-locked host buffers itself (mapped / UVA access; nothing to wait for around it);
- *   -k      outputs direct, actions through a k-chunk H2D copy pipeline.
- * The direct modes need page-locked buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory); for
- * pageable buffers the call silently uses the copy pipeline.
+ *   <= 0    direct: ONE kernel over all envs reads the actions from, and writes the rewards to, the caller's
+ *           page-locked host buffers itself (mapped / UVA access: no copy to wait for before or after the
+ *           kernel, no cross-engine dependency); the one-byte-per-env dones stay a device tensor followed by
+ *           one small copy (single-byte stores over PCIe cost more than the whole rest of the step). Needs
+ *           cudaHostAlloc / cudaHostRegister / torch pin_memory buffers, else falls back to k = 1.
  * On failure nothing is left allocated and *out is NULL. */
 int wh_env_create(const wh_config *cfg, int64_t n_envs, int device, int64_t env_id0, uint64_t seed,
                   int n_chunks, wh_env **out);

@@ -813,8 +813,8 @@ struct wh_env {
     wh_config cfg;
     int64_t N, env_id0;
     uint64_t seed;
-    int device, n_chunks, R, P;
-    int direct;      // 0 = copy pipeline; 1 = the kernel reads actions from / writes rewards + dones to the host buffers; 2 = outputs only
+    int device, n_chunks, n_streams, R, P;
+    int direct;      // 0 = copy pipeline; 1 = the kernel reads the actions from / writes the rewards to the host buffers itself
     wh_state st;
     wh_obs obs;
     int32_t *d_actions;
@@ -860,9 +860,10 @@ static int env_alloc(wh_env *E, const KParams &K, int n_chunks) {
     CK(cudaMalloc(&E->d_actions, N * R * 4)); CK(cudaMalloc(&E->d_rewards, N * R * 4));
     CK(cudaMalloc(&E->d_dones, N)); CK(cudaMalloc(&E->d_stats, WH_NUM_STATS * 8));
     CK(cudaMemset(E->d_stats, 0, WH_NUM_STATS * 8));
-    E->streams = (cudaStream_t *)calloc((size_t)n_chunks, sizeof(cudaStream_t));
+    E->n_streams = n_chunks < 1 ? 1 : n_chunks;
+    E->streams = (cudaStream_t *)calloc((size_t)E->n_streams, sizeof(cudaStream_t));
     if (!E->streams) return WH_E_ARG;
-    for (int i = 0; i < n_chunks; ++i) CK(cudaStreamCreateWithFlags(&E->streams[i], cudaStreamNonBlocking));
+    for (int i = 0; i < E->n_streams; ++i) CK(cudaStreamCreateWithFlags(&E->streams[i], cudaStreamNonBlocking));
     CK(cudaDeviceSynchronize());
     return 0;
 }
@@ -879,11 +880,9 @@ int wh_env_create(const wh_config *cfg, int64_t n_envs, int device, int64_t env_
     memset(E, 0, sizeof(*E));
     E->cfg = *cfg; E->N = n_envs; E->env_id0 = env_id0; E->seed = seed; E->device = device;
     E->R = K.R; E->P = K.P;
-    // n_chunks <= 0 selects the direct (zero-copy) modes, see wh_env_step_host: 0 = inputs and outputs,
-    // -k = outputs only, inputs through a k-chunk copy pipeline
-    E->direct = n_chunks == 0 ? 1 : (n_chunks < 0 ? 2 : 0);
-    if (n_chunks == 0) n_chunks = 1;
-    if (n_chunks < 0) n_chunks = -n_chunks;
+    // n_chunks <= 0 selects the direct (zero-copy) mode, see wh_env_step_host
+    E->direct = n_chunks <= 0 ? 1 : 0;
+    if (n_chunks <= 0) n_chunks = 1;
     if (n_chunks > 64) n_chunks = 64;
     E->n_chunks = n_chunks;
     if (int rc = env_alloc(E, K, n_chunks)) {   // a failed allocation leaves nothing behind
@@ -905,7 +904,7 @@ void wh_env_destroy(wh_env *E) {
                     E->d_actions, E->d_rewards, E->d_dones, E->d_stats};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (E->streams) {
-        for (int i = 0; i < E->n_chunks; ++i) if (E->streams[i]) cudaStreamDestroy(E->streams[i]);
+        for (int i = 0; i < E->n_streams; ++i) if (E->streams[i]) cudaStreamDestroy(E->streams[i]);
         free(E->streams);
     }
     delete E;
@@ -939,21 +938,22 @@ static int env_step_issue(wh_env *E, const int32_t *actions, float *rewards, uin
     // straight into the caller's page-locked buffers (and, mode 1, reads the actions from them), so there is
     // no separate copy to wait for before / after the kernel. Falls back to the copy pipeline when a buffer
     // is not page-locked.
-    void *d_act = nullptr, *d_rew = nullptr, *d_done = nullptr;
-    const bool out_direct = E->direct && device_can_address(rewards, &d_rew) && device_can_address(dones, &d_done);
-    const bool in_direct = out_direct && E->direct == 1 && (greedy || device_can_address(actions, &d_act));
-    if (out_direct && in_direct) {
+    void *d_act = nullptr, *d_rew = nullptr;
+    if (E->direct && device_can_address(rewards, &d_rew) && (greedy || device_can_address(actions, &d_act))) {
         cudaStream_t s = E->streams[0];
         int rc;
         const int fl = WH_FLAG_AUTO_RESET | (compact ? WH_FLAG_COMPACT_IO : 0);
+        // dones (one byte per env) stay a device-side tensor + one small copy: single-byte stores over PCIe
+        // are the one thing the direct mode must not do (262 144 one-byte write transactions per step)
         if (greedy)
             rc = wh_greedy_step(&E->cfg, &E->st, E->N, E->env_id0, E->seed, E->seed ^ 0x5EEDull, 0, nullptr,
-                                (float *)d_rew, (uint8_t *)d_done, E->d_stats, &E->obs, fl, s);
+                                (float *)d_rew, E->d_dones, E->d_stats, &E->obs, fl, s);
         else
             rc = wh_step(&E->cfg, &E->st, E->N, E->env_id0, E->seed, (const int32_t *)d_act, nullptr, nullptr, nullptr,
-                         (float *)d_rew, (uint8_t *)d_done, E->d_stats, &E->obs, fl, nullptr, s);
+                         (float *)d_rew, E->d_dones, E->d_stats, &E->obs, fl, nullptr, s);
         E->launches += 1;
         if (rc) return rc;
+        CK(cudaMemcpyAsync(dones, E->d_dones, (size_t)E->N, cudaMemcpyDeviceToHost, s));
         if (obs_host) {
             const wh_obs &ob = E->obs; const wh_obs &oh = *obs_host; const int64_t n = E->N;
             CK(cudaMemcpyAsync(oh.num_agents, ob.num_agents, n * R * 4, cudaMemcpyDeviceToHost, s));
@@ -988,8 +988,7 @@ static int env_step_issue(wh_env *E, const int32_t *actions, float *rewards, uin
             } else {
                 CK(cudaMemcpyAsync(E->d_actions + e0 * R, actions + e0 * R, n * R * 4, cudaMemcpyHostToDevice, s));
                 rc = wh_step(&E->cfg, &st, n, E->env_id0 + e0, E->seed, E->d_actions + e0 * R, nullptr, nullptr,
-                             nullptr, out_direct ? (float *)d_rew + e0 * R : E->d_rewards + e0 * R,
-                             out_direct ? (uint8_t *)d_done + e0 : E->d_dones + e0, E->d_stats, &ob,
+                             nullptr, E->d_rewards + e0 * R, E->d_dones + e0, E->d_stats, &ob,
                              WH_FLAG_AUTO_RESET | WH_FLAG_NO_PDL, nullptr, s);
             }
         }
@@ -998,10 +997,9 @@ static int env_step_issue(wh_env *E, const int32_t *actions, float *rewards, uin
         if (compact)
             CK(cudaMemcpyAsync(reinterpret_cast<uint8_t *>(rewards) + e0 * R, reinterpret_cast<uint8_t *>(E->d_rewards) + e0 * R,
                                n * R, cudaMemcpyDeviceToHost, s));
-        else if (!out_direct || greedy)
+        else
             CK(cudaMemcpyAsync(rewards + e0 * R, E->d_rewards + e0 * R, n * R * 4, cudaMemcpyDeviceToHost, s));
-        if (compact || !out_direct || greedy)
-            CK(cudaMemcpyAsync(dones + e0, E->d_dones + e0, n, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(dones + e0, E->d_dones + e0, n, cudaMemcpyDeviceToHost, s));
         if (obs_host) {
             const wh_obs oh = offset_obs(*obs_host, e0, R);
             CK(cudaMemcpyAsync(oh.num_agents, ob.num_agents, n * R * 4, cudaMemcpyDeviceToHost, s));
@@ -1023,7 +1021,7 @@ static int env_step_impl(wh_env *E, const int32_t *actions, float *rewards, uint
                          const wh_obs *obs_host, bool greedy, bool compact = false) {
     if (!E || !rewards || !dones || (!greedy && !actions)) return WH_E_ARG;
     int rc = env_step_issue(E, actions, rewards, dones, obs_host, greedy, compact);
-    for (int c = 0; c < E->n_chunks; ++c) {
+    for (int c = 0; c < E->n_streams; ++c) {
         const cudaError_t e = cudaStreamSynchronize(E->streams[c]);
         if (!rc && e != cudaSuccess) rc = (int)e;
     }

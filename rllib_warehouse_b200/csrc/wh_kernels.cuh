@@ -1139,7 +1139,9 @@ __device__ __forceinline__ int greedy_from_state(const KParams &P, const Group<G
     // lane r takes the r-th active pickup point's cell
     const int nact = __popcll(active);
     uint32_t cell = geo.null16();
-    if (g.gl < nact && g.gl < R) cell = pickup_cell16(P, geo, nth_set64<Group<GC>::PBITS>(active, g.gl));
+    if (g.gl < nact && g.gl < R)
+        cell = pickup_cell16(P, geo, (RC != 0 && RC <= 4) ? nth_set_small<(RC ? RC : 1)>((uint32_t)active, g.gl)
+                                                          : nth_set64<Group<GC>::PBITS>(active, g.gl));
     // L1 argmin with first-minimum tie-break (solvers.py:53-58) as a running minimum of the key
     // distance << 21 | request index << 16 | cell. The distance of two packed cells (x | y << 8, upper
     // bytes zero) is ONE instruction: the byte-wise sum of absolute differences (VABSDIFF4.U8.ACC).

@@ -26,7 +26,7 @@ class _CudaView:
 
 class HostWarehouse:
     def __init__(self, config: WarehouseConfig, num_envs: int, device: int = 0, seed: int = 0,
-                 env_id0: int = 0, chunks: int = 8, compact: bool = False):
+                 env_id0: int = 0, chunks: int = 0, compact: bool = False):
         if not torch.cuda.is_available():
             raise nv.NativeError("HostWarehouse needs a CUDA device: there is no CPU fallback")
         self.lib, self.config = nv.lib(), config
