@@ -107,7 +107,9 @@ __device__ __forceinline__ void account_episode(const KParams &P, bool owner, en
 // auto-reset) — core.py:262-442, solvers.py:27-58
 // PLAIN: the caller passes int32 actions / float32 rewards, no dict order and no replayed draws (the
 // throughput path); the instantiation then carries none of the code or tests for those options.
-template <int GC, int RC, bool GREEDY, bool FLAT, bool PLAIN = false>
+// KEEP (PLAIN only): the state is loaded / stored with the L2 evict_last priority (1 = all accesses, 2 = half),
+// see wh_kernels.cuh.
+template <int GC, int RC, bool GREEDY, bool FLAT, bool PLAIN = false, int KEEP = 0>
 __global__ void __launch_bounds__(BLOCK, (RC == 16 ? WH_MIN_BLOCKS_LARGE : RC == 9 ? WH_MIN_BLOCKS_MEDIUM : RC == 4 ? WH_MIN_BLOCKS_SMALL : WH_MIN_BLOCKS)) k_step(const __grid_constant__ KParams P) {
     __shared__ __align__(16) unsigned char smem[StageMem<GC, RC, FLAT>::BYTES];
     // Programmatic dependent launch (launch_step): the next step's blocks may be scheduled while
@@ -121,11 +123,11 @@ __global__ void __launch_bounds__(BLOCK, (RC == 16 ? WH_MIN_BLOCKS_LARGE : RC ==
     const uint32_t env_id = (uint32_t)P.env_id0 + e;
     EnvRegs s;
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    load_env(P, g, e, R, (RC ? 4 * GC : P.P), s);
+    load_env<GC, KEEP>(P, g, e, R, (RC ? 4 * GC : P.P), s);
     int4 acc4 = make_int4(0, 0, 0, 0);
     bool acc_dirty = false;
     constexpr bool EARLY_ACC = RC != 4;
-    if (EARLY_ACC && g.gl == 0) acc4 = reinterpret_cast<const int4 *>(P.acc)[e];   // with the rest of the state, see account_episode
+    if (EARLY_ACC && g.gl == 0) acc4 = ld_state<KEEP>(reinterpret_cast<const int4 *>(P.acc) + e);   // with the rest of the state, see account_episode
 
     // envs masked out of this step (BaseEnv.send_actions for a subset of the envs) compute along but write nothing
     const bool live = t.live && (PLAIN || !P.env_mask || P.env_mask[e] != 0);
@@ -154,7 +156,7 @@ __global__ void __launch_bounds__(BLOCK, (RC == 16 ? WH_MIN_BLOCKS_LARGE : RC ==
     }
     const bool auto_reset = (P.flags & WH_FLAG_AUTO_RESET) != 0;
     account_episode<EARLY_ACC>(P, g.gl == 0 && live, e, so, s, done, auto_reset, acc4, acc_dirty);
-    if (acc_dirty) reinterpret_cast<int4 *>(P.acc)[e] = acc4;
+    if (acc_dirty) st_state<KEEP>(reinterpret_cast<int4 *>(P.acc) + e, acc4);
     int flavour = WH_OBS_STEP;
     bool meta = false;
     if (auto_reset && __any_sync(FULL, done)) {
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(BLOCK, (RC == 16 ? WH_MIN_BLOCKS_LARGE : RC ==
         if (done) { active = a2; flavour = WH_OBS_RESET; }
         meta = true;
     }
-    if (live) store_env(P, g, e, R, (RC ? 4 * GC : P.P), s, meta);
+    if (live) store_env<GC, KEEP>(P, g, e, R, (RC ? 4 * GC : P.P), s, meta);
     if constexpr (FLAT)   // RLlib-flattened float32 layout instead of the dict keys (separate instantiation)
         build_obs_flat<GC, RC>(P, g, e, R, s, active, tpos16, flavour, live, P.flat_out,
                                reinterpret_cast<float *>(StageMem<GC, RC, true>::mine(smem, g)),
@@ -507,21 +509,36 @@ static void launch_kind(Kind kind, const KParams &K, cudaStream_t s) {
             cudaFuncSetAttribute(k_step<GC, RC, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
             cudaFuncSetAttribute(k_step<GC, RC, false, false, RC != 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
             cudaFuncSetAttribute(k_step<GC, RC, true, false, RC != 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+            cudaFuncSetAttribute(k_step<GC, RC, false, false, RC != 0, (RC != 0 ? 1 : 0)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+            cudaFuncSetAttribute(k_step<GC, RC, true, false, RC != 0, (RC != 0 ? 1 : 0)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
             done[dev].store(true, std::memory_order_release);
         }
     }
     const bool plain = RC != 0 && !(K.flags & WH_FLAG_COMPACT_IO) && !K.order && !K.spawn_p && !K.env_mask;
+    // KEEP variant: the whole state of this launch (narrow state + episode counters) fits the keep budget
+    const double state_mb = (double)K.N * (3.0 * K.R + 3.0 * K.P + 9.0 + 16.0) / 1048576.0;
+    static const double keep_mb = [] { const char *v = getenv("WH_B200_KEEP_MB"); return v ? atof(v) : (double)WH_KEEP_MAX_MB; }();
+    // level 1 while the state fits the budget; Medium also pays at level 2 (half) up to twice the budget
+    const int keep = !(plain && (RC == 9 || RC == 16)) ? 0 : state_mb <= keep_mb ? 1 : (RC == 9 && state_mb <= 2 * keep_mb) ? 2 : 0;
+    constexpr bool KV = RC == 9 || RC == 16;      // the KEEP instantiations exist for Medium and Large only
+    constexpr int K1 = KV ? 1 : 0, K2 = RC == 9 ? 2 : 0;
     switch (kind) {
     case K_STEP:
-        if (plain) launch_step(k_step<GC, RC, false, false, RC != 0>, grid, dyn, s, K);
+        if (keep == 2) launch_step(k_step<GC, RC, false, false, KV, K2>, grid, dyn, s, K);
+        else if (keep) launch_step(k_step<GC, RC, false, false, KV, K1>, grid, dyn, s, K);
+        else if (plain) launch_step(k_step<GC, RC, false, false, RC != 0>, grid, dyn, s, K);
         else launch_step(k_step<GC, RC, false, false>, grid, dyn, s, K);
         break;
     case K_GSTEP:
-        if (plain) launch_step(k_step<GC, RC, true, false, RC != 0>, grid, dyn, s, K);
+        if (keep == 2) launch_step(k_step<GC, RC, true, false, KV, K2>, grid, dyn, s, K);
+        else if (keep) launch_step(k_step<GC, RC, true, false, KV, K1>, grid, dyn, s, K);
+        else if (plain) launch_step(k_step<GC, RC, true, false, RC != 0>, grid, dyn, s, K);
         else launch_step(k_step<GC, RC, true, false>, grid, dyn, s, K);
         break;
     case K_STEP_FLAT:
-        if (plain) launch_step(k_step<GC, RC, false, true, RC != 0>, grid, 0, s, K);
+        if (keep == 2) launch_step(k_step<GC, RC, false, true, KV, K2>, grid, 0, s, K);
+        else if (keep) launch_step(k_step<GC, RC, false, true, KV, K1>, grid, 0, s, K);
+        else if (plain) launch_step(k_step<GC, RC, false, true, RC != 0>, grid, 0, s, K);
         else launch_step(k_step<GC, RC, false, true>, grid, 0, s, K);
         break;
     case K_RESET: k_reset<GC, RC><<<grid, BLOCK, 0, s>>>(K); break;

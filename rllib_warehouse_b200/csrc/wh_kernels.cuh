@@ -29,6 +29,93 @@ namespace wh {
 // e*R*R) then stays a single IMAD / IMAD.WIDE.U32; the launchers reject N*R*R >= 2^32.
 typedef uint32_t env_t;
 
+// L2 eviction priority for the STATE (createpolicy + .L2::cache_hint; the policy rides in the memory
+// descriptor, no extra instruction per access). The state — a few tens of MB — is written by step t and read
+// back by step t+1, but the 0.2 - 2.2 GB observation stream of a step pushes it out of the 126 MB L2 in
+// between, so every step starts with DRAM-latency loads queued behind the write stream (the largest single
+// stall of the step kernels, profiles/r02_hotspots_*.txt). Loading and storing the state evict_last keeps it
+// resident: Medium 65 536 envs 0.855 -> 0.924 of the HBM peak, 131 072 envs 0.903 -> 0.953, Large 65 536 envs
+// 0.966 -> 1.004. It costs L2 capacity the write-back path also wants, so it only pays while the state is
+// small against L2: at 262 144 envs (37 / 64 MB) it is -0.4 % / -1.3 %, and Small (whose 143 MB observation
+// stream leaves the state in L2 anyway) loses 3.6 %. A FRACTIONAL policy (half of the accesses evict_last)
+// still pays for Medium at 37 MB (0.923 -> 0.939) but not for Large at 64 MB (-0.6 .. -1.5 %). Hence
+// compile-time variants of the throughput (PLAIN) kernels — KEEP = 1 (all) / 2 (half) — that the launcher
+// selects from the state size (WH_KEEP_MAX_MB, and twice that for the half policy of Medium). Observation
+// stores with evict_first were measured too: -4 % everywhere, not used.
+#ifndef WH_KEEP_MAX_MB
+#define WH_KEEP_MAX_MB 32
+#endif
+// KEEP levels: 0 = plain accesses, 1 = every state access evict_last, 2 = half of them (fractional policy)
+template <int KEEP>
+__device__ __forceinline__ uint64_t l2_evict_last() {
+    uint64_t p;
+    if constexpr (KEEP == 2) asm("createpolicy.fractional.L2::evict_last.b64 %0, 0.5;" : "=l"(p));
+    else asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
+template <typename T>
+__device__ __forceinline__ void st_hint(T *p, const T &v, uint64_t pol) {
+    static_assert(sizeof(T) == 16 || sizeof(T) == 8 || sizeof(T) == 4 || sizeof(T) == 2 || sizeof(T) == 1, "store width");
+    if constexpr (sizeof(T) == 16) {
+        const uint4 u = *reinterpret_cast<const uint4 *>(&v);
+        asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w), "l"(pol) : "memory");
+    } else if constexpr (sizeof(T) == 8) {
+        const uint2 u = *reinterpret_cast<const uint2 *>(&v);
+        asm volatile("st.global.L2::cache_hint.v2.b32 [%0], {%1,%2}, %3;" ::"l"(p), "r"(u.x), "r"(u.y), "l"(pol) : "memory");
+    } else if constexpr (sizeof(T) == 4) {
+        const uint32_t u = *reinterpret_cast<const uint32_t *>(&v);
+        asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(p), "r"(u), "l"(pol) : "memory");
+    } else if constexpr (sizeof(T) == 2) {
+        const uint16_t u = *reinterpret_cast<const uint16_t *>(&v);
+        asm volatile("st.global.L2::cache_hint.b16 [%0], %1, %2;" ::"l"(p), "h"(u), "l"(pol) : "memory");
+    } else {
+        const uint32_t u = *reinterpret_cast<const uint8_t *>(&v);
+        asm volatile("st.global.L2::cache_hint.b8 [%0], %1, %2;" ::"l"(p), "r"(u), "l"(pol) : "memory");
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ T ld_hint(const T *p, uint64_t pol) {
+    static_assert(sizeof(T) == 16 || sizeof(T) == 8 || sizeof(T) == 4 || sizeof(T) == 2 || sizeof(T) == 1, "load width");
+    T out;
+    if constexpr (sizeof(T) == 16) {
+        uint4 u;
+        asm("ld.global.L2::cache_hint.v4.b32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(p), "l"(pol));
+        out = *reinterpret_cast<T *>(&u);
+    } else if constexpr (sizeof(T) == 8) {
+        uint2 u;
+        asm("ld.global.L2::cache_hint.v2.b32 {%0,%1}, [%2], %3;" : "=r"(u.x), "=r"(u.y) : "l"(p), "l"(pol));
+        out = *reinterpret_cast<T *>(&u);
+    } else if constexpr (sizeof(T) == 4) {
+        uint32_t u;
+        asm("ld.global.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(u) : "l"(p), "l"(pol));
+        out = *reinterpret_cast<T *>(&u);
+    } else if constexpr (sizeof(T) == 2) {
+        uint16_t u;
+        asm("ld.global.L2::cache_hint.b16 %0, [%1], %2;" : "=h"(u) : "l"(p), "l"(pol));
+        out = *reinterpret_cast<T *>(&u);
+    } else {
+        uint32_t u;
+        asm("ld.global.L2::cache_hint.b8 %0, [%1], %2;" : "=r"(u) : "l"(p), "l"(pol));
+        const uint8_t b = (uint8_t)u;
+        out = *reinterpret_cast<const T *>(&b);
+    }
+    return out;
+}
+
+// state accessors
+template <int KEEP, typename T>
+__device__ __forceinline__ T ld_state(const T *p) {
+    if constexpr (KEEP != 0) return ld_hint(p, l2_evict_last<KEEP>());
+    else return *p;
+}
+template <int KEEP, typename T>
+__device__ __forceinline__ void st_state(T *p, const T &v) {
+    if constexpr (KEEP != 0) st_hint(p, v, l2_evict_last<KEEP>());
+    else *p = v;
+}
+
 template <bool STREAM, typename T>
 __device__ __forceinline__ void st_obs(T *p, const T &v) {
     if (STREAM) __stcs(p, v);
@@ -319,39 +406,39 @@ __device__ __forceinline__ void set_timer(EnvRegs &s, int j, uint32_t v) {
 }
 
 // PP = number of pickup points: a compile-time 4*G in the variant kernels, P.P otherwise
-template <int GC>
+template <int GC, int KEEP = 0>
 __device__ __forceinline__ void load_env(const KParams &P, const Group<GC> &g, env_t e, int R, int PP, EnvRegs &s) {
-    s.time = P.time[e];
-    s.A = P.num_agents[e];
-    s.ep = P.episode_ctr[e];
+    s.time = ld_state<KEEP>(P.time + e);
+    s.A = ld_state<KEEP>(P.num_agents + e);
+    s.ep = ld_state<KEEP>(P.episode_ctr + e);
     s.pos16 = 0xFFFFu;
     s.atgt = -1;
     if (g.gl < R) {
-        s.pos16 = reinterpret_cast<const uint16_t *>(P.agent_pos)[e * R + g.gl];
-        s.atgt = P.agent_tgt[e * R + g.gl];
+        s.pos16 = ld_state<KEEP>(reinterpret_cast<const uint16_t *>(P.agent_pos) + e * R + g.gl);
+        s.atgt = ld_state<KEEP>(P.agent_tgt + e * R + g.gl);
     }
     s.pt4 = 0xFFFFFFFFu;
     s.tmr = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
     if (4 * g.gl < PP) {
-        s.pt4 = reinterpret_cast<const uint32_t *>(P.pickup_tgt + e * PP)[g.gl];
-        s.tmr = reinterpret_cast<const uint2 *>(P.pickup_timer + e * PP)[g.gl];
+        s.pt4 = ld_state<KEEP>(reinterpret_cast<const uint32_t *>(P.pickup_tgt + e * PP) + g.gl);
+        s.tmr = ld_state<KEEP>(reinterpret_cast<const uint2 *>(P.pickup_timer + e * PP) + g.gl);
     }
 }
 
-template <int GC>
+template <int GC, int KEEP = 0>
 __device__ __forceinline__ void store_env(const KParams &P, const Group<GC> &g, env_t e, int R, int PP,
                                           const EnvRegs &s, bool store_meta) {
     if (g.gl < R) {
-        reinterpret_cast<uint16_t *>(P.agent_pos)[e * R + g.gl] = (uint16_t)s.pos16;
-        P.agent_tgt[e * R + g.gl] = (int8_t)s.atgt;
+        st_state<KEEP>(reinterpret_cast<uint16_t *>(P.agent_pos) + e * R + g.gl, (uint16_t)s.pos16);
+        st_state<KEEP>(P.agent_tgt + e * R + g.gl, (int8_t)s.atgt);
     }
     if (4 * g.gl < PP) {
-        reinterpret_cast<uint32_t *>(P.pickup_tgt + e * PP)[g.gl] = s.pt4;
-        reinterpret_cast<uint2 *>(P.pickup_timer + e * PP)[g.gl] = s.tmr;
+        st_state<KEEP>(reinterpret_cast<uint32_t *>(P.pickup_tgt + e * PP) + g.gl, s.pt4);
+        st_state<KEEP>(reinterpret_cast<uint2 *>(P.pickup_timer + e * PP) + g.gl, s.tmr);
     }
     if (g.gl == 0) {
-        P.time[e] = s.time;
-        if (store_meta) { P.num_agents[e] = (int8_t)s.A; P.episode_ctr[e] = s.ep; }
+        st_state<KEEP>(P.time + e, s.time);
+        if (store_meta) { st_state<KEEP>(P.num_agents + e, (int8_t)s.A); st_state<KEEP>(P.episode_ctr + e, s.ep); }
     }
 }
 
