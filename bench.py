@@ -62,6 +62,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (solver kernel, configs[2])")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin each rank to its GPU's NUMA node")
     ap.add_argument("--seed", type=int, default=20261018)
     return ap.parse_args()
 
@@ -256,6 +257,10 @@ def run_b200(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_node = None
+    if world > 1 and not args.no_numa_bind:
+        from rllib_warehouse_b200.parallel import bind_to_gpu_numa_node
+        numa_node = bind_to_gpu_numa_node(local)     # page-locked host buffers local to this GPU's PCIe root
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     A = VARIANT_AGENTS[args.variant]
@@ -389,7 +394,7 @@ def run_b200(args):
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "int32",
         "data": "synthetic", "config": workload_config(args, world),
         "roofline": roofline, "gpu_launches": gpu_launches, "launches_per_step": launches_per_step,
-        "collective_ms": coll_ms, "collective_api": coll_api,
+        "collective_ms": coll_ms, "collective_api": coll_api, "numa_node_rank0": numa_node,
         "clocks": clocks.summary(),
     }
 
@@ -459,6 +464,7 @@ def run_b200(args):
                 "api": api + "; C ABI, pinned host buffers",
                 "reward_checksum": float(host_rewards.sum()), "gpu_launches": launches,
             }
+            res["pcie_GBps_per_gpu"] = (res["h2d_bytes_per_step"] + res["d2h_bytes_per_step"]) / (dt / steps) / 1e9
             if host_obs:
                 res["d2h_GBps"] = res["d2h_bytes_per_step"] / (dt / steps) / 1e9
                 res["obs_checksum"] = int(keep["requests"].sum())
@@ -470,6 +476,10 @@ def run_b200(args):
         ch = args.e2e_chunks
         out["e2e"] = run_e2e("ref_dtypes", 0 if ch is None else ch, args.e2e_steps)
         out["e2e_alt"] = run_e2e("compact", 0 if ch is None else ch, args.e2e_steps)
+        if world > 1:
+            out["e2e_note"] = ("all ranks move their host buffers at the same time: on a box whose GPUs share host-side PCIe "
+                               "uplinks / memory fabric the int32/float32 format (33.8 MB per GPU and step) is bound by that shared "
+                               "fabric, whatever the transport (profiles/README.md); see pcie_GBps_per_gpu")
         if world == 1:
             try:
                 out["e2e_copy_pipeline"] = run_e2e("ref_dtypes", 8, args.e2e_steps)

@@ -18,6 +18,32 @@ def shard_range(num_envs_total: int, rank: int, world: int):
     return lo, hi
 
 
+def bind_to_gpu_numa_node(device_index: int):
+    """Pins this process to the CPUs of the NUMA node its GPU hangs off (sysfs: the PCI device's `numa_node`
+    and the node's `cpulist`), so that page-locked host buffers allocated afterwards are local to the GPU's
+    PCIe root. torchrun does not do this; without it half the ranks of a two-socket box reach their host
+    buffers across the socket interconnect. Returns the node id, or None when it cannot be determined."""
+    try:
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = torch.cuda.get_device_properties(device_index).pci_domain_id
+        dev = torch.cuda.get_device_properties(device_index).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def init_from_env(backend=None, device=None):
     """Reads RANK / WORLD_SIZE / MASTER_* (torchrun contract). Returns (rank, world)."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
