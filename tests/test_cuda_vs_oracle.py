@@ -632,3 +632,66 @@ def test_multi_step_greedy_equals_single_launches(size, n, p):
         for k in one.obs:
             assert torch.equal(one.obs[k], many.obs[k]), (chunk, k)
     assert torch.equal(one.stats, many.stats) and int(one.stats[0]) == 2 * n
+
+
+@pytest.mark.parametrize("keep_mb,what", [("0", "plain PLAIN kernels"), ("0.1", "half evict_last policy (KEEP = 2)"),
+                                          ("1000", "full evict_last policy (KEEP = 1)")])
+def test_l2_keep_variants_are_bit_exact(keep_mb, what):
+    """The throughput kernels exist in three L2-policy variants for the state accesses (plain / evict_last /
+    half evict_last), selected from the state size (WH_KEEP_MAX_MB; WH_B200_KEEP_MB overrides, read once per
+    process — hence a subprocess). All three must give the oracle's results: Medium and Large, random actions
+    and the in-kernel solver, flat observations, across an episode boundary."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import sys, os
+sys.path.insert(0, os.path.join(os.getcwd(), "tests")); sys.path.insert(0, os.getcwd())
+import numpy as np, torch
+import golden_util as gu
+from oracle import wh_oracle as wo
+from rllib_warehouse_b200 import VARIANTS, BatchedWarehouse
+for size, n in (("medium", 1000), ("large", 400)):
+    kw = dict(wo.VARIANTS[size]); kw["episode"] = 25
+    cfg = VARIANTS[size].replace(episode_duration=25)
+    gpu = BatchedWarehouse(cfg, n, seed=3, auto_reset=True)
+    fused = BatchedWarehouse(cfg, n, seed=3, auto_reset=True)
+    cpu = wo.OracleEnv(wo.make_config(**kw), n, seed=3)
+    gpu.reset(); fused.reset(); cpu.reset()
+    rng = np.random.Generator(np.random.PCG64(1))
+    for t in range(60):
+        a = rng.integers(0, 9, size=(n, cpu.R)).astype(np.int32)
+        if t % 3 == 2:
+            flat, rew, dones = gpu.step_flat(torch.from_numpy(a).cuda())
+        else:
+            _, rew, dones = gpu.step(torch.from_numpy(a).cuda())          # device int32 actions: the PLAIN path
+        cpu.step(a, with_obs=False)
+        assert np.array_equal(rew.cpu().numpy(), cpu.rewards) and np.array_equal(dones.cpu().numpy(), cpu.dones), (size, t)
+        done = cpu.dones.astype(bool)
+        cpu.build_obs(0)
+        if done.any():
+            keep = {k: v.copy() for k, v in cpu.obs.items()}
+            cpu.reset(env_mask=done.astype(np.uint8)); cpu.state["acc"][done] = 0
+            for k in cpu.obs: cpu.obs[k][~done] = keep[k][~done]
+        st = gpu.get_state()
+        for k in gu.STATE_KEYS + ("episode", "acc"):
+            assert np.array_equal(st[k].reshape(cpu.state[k].shape), cpu.state[k]), (size, t, k)
+        if t % 3 == 2:
+            want = np.concatenate([cpu.obs[k].reshape(n, cpu.R, -1).astype(np.float32) for k in sorted(cpu.obs)], axis=2)
+            assert np.array_equal(flat.cpu().numpy(), want), (size, t)
+        else:
+            for k in gu.OBS_KEYS:
+                assert np.array_equal(gpu.obs[k].cpu().numpy().astype(np.int32), cpu.obs[k].astype(np.int32)), (size, t, k)
+    twin = BatchedWarehouse(cfg, n, seed=3, auto_reset=True); twin.reset()
+    for t in range(40):                                                     # in-kernel solver (K_GSTEP variants) vs solver kernel + step
+        fused.greedy_step(want_actions=False)
+        twin.step(twin.greedy_actions())
+        for k in fused.state:
+            assert torch.equal(fused.state[k], twin.state[k]), (size, t, k)
+    assert torch.equal(fused.stats, twin.stats)
+print("keep variants ok")
+"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=root,
+                         env=dict(os.environ, WH_B200_KEEP_MB=keep_mb))
+    assert res.returncode == 0 and "keep variants ok" in res.stdout, what + "\n" + res.stdout[-1000:] + res.stderr[-3000:]
