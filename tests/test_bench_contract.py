@@ -65,3 +65,34 @@ def test_cuda_arm_needs_a_gpu():
                          capture_output=True, text=True, timeout=300)
     assert res.returncode != 0 and res.stdout.strip() == ""
     assert "no CPU fallback" in res.stderr or "CUDA" in res.stderr
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_cuda_arm_json_contract_on_a_small_workload():
+    """The CUDA arm end to end on a reduced workload (the full one is the driver's): one JSON line with the
+    contract's keys — roofline (bound, achieved, peak, frac, traffic), the three e2e consumers with their copied
+    bytes, cpu_baseline with a kind, clocks, and exactly one kernel launch per timed step."""
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "6", "--warmup", "3", "--envs", "8192",
+                          "--e2e-steps", "6", "--cpu-seconds", "2", "--cpu-envs", "256", "--no-extras"],
+                         capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stderr[-3000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["metric"] == "agent_steps_per_sec" and d["unit"] == "agent-steps/s" and d["n_gpus"] == 1
+    assert d["steps"] == 6 and d["warmup"] == 3 and d["gpu_launches"] == 6 and d["launches_per_step"] == 1
+    assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None and d["dtype"] == "int32"
+    assert d["config"]["workload"] == "warehouse-large-8192-envs-per-gpu" and d["config"]["envs_total"] == 8192
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["peak"] > 1000 and 0 < r["frac"] < 1.3
+    assert abs(r["achieved"] - r["alg_bytes_per_launch"] / (r["kernel_ms_avg"] * 1e-3) / 1e9) < 1e-6 * r["achieved"]
+    assert r["alg_bytes_per_launch"] == 9147 * 8192 and "traffic" in r and "traffic_source" in r
+    for k, h2d, d2h in (("e2e", 8192 * 16 * 4, 8192 * 16 * 4 + 8192), ("e2e_alt", 8192 * 16, 8192 * 16 + 8192)):
+        assert d[k]["value"] > 0 and d[k]["h2d_bytes_per_step"] == h2d and d[k]["d2h_bytes_per_step"] == d2h
+        assert d[k]["value"] != d["value"] and d[k]["gpu_launches"] >= 6
+    assert d["e2e_host_obs"]["d2h_bytes_per_step"] > 8192 * 8512 and d["e2e_copy_pipeline"]["chunks"] == 8
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] > 0
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"} and "collective_ms" in d
