@@ -132,8 +132,9 @@ __global__ void __launch_bounds__(BLOCK, (RC == 16 ? WH_MIN_BLOCKS_LARGE : RC ==
     // envs masked out of this step (BaseEnv.send_actions for a subset of the envs) compute along but write nothing
     const bool live = t.live && (PLAIN || !P.env_mask || P.env_mask[e] != 0);
     int act = -1, ord = -1;
+    unsigned long long active0 = 0ull;
     if (GREEDY) {
-        act = greedy_from_state<GC, RC>(P, g, R, env_id, s);
+        act = greedy_from_state<GC, RC>(P, g, R, env_id, s, active0);
         if (P.actions_out && live && g.gl < R) P.actions_out[e * R + g.gl] = act;
     } else if (g.gl < R) {
         act = (!PLAIN && (P.flags & WH_FLAG_COMPACT_IO)) ? (int)reinterpret_cast<const int8_t *>(P.actions)[e * R + g.gl]
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(BLOCK, (RC == 16 ? WH_MIN_BLOCKS_LARGE : RC ==
     }
     s.time += 1;                                                               // core.py:267
     do_moves<GC, RC>(P, g, R, s.A, act, ord, !PLAIN && !GREEDY && P.order != nullptr, s.pos16);
-    const StepOut so = do_world(P, g, e, R, env_id, s, !PLAIN && !GREEDY && P.spawn_p != nullptr);
+    const StepOut so = do_world(P, g, e, R, env_id, s, !PLAIN && !GREEDY && P.spawn_p != nullptr, active0, GREEDY);
     unsigned long long active = so.active;
     uint32_t tpos16 = so.tpos16;
 
@@ -194,10 +195,11 @@ __global__ void __launch_bounds__(BLOCK, (RC == 16 ? 4 : WH_MIN_BLOCKS)) k_rollo
     bool acc_dirty = false;
     if (g.gl == 0) acc4 = reinterpret_cast<const int4 *>(P.acc)[e];
     for (int it = 0; it < P.n_steps; ++it) {
-        const int act = greedy_from_state<GC, RC>(P, g, R, env_id, s);
+        unsigned long long active0;
+        const int act = greedy_from_state<GC, RC>(P, g, R, env_id, s, active0);
         s.time += 1;                                                           // core.py:267
         do_moves<GC, RC>(P, g, R, s.A, act, -1, false, s.pos16);
-        const StepOut so = do_world(P, g, e, R, env_id, s, false);
+        const StepOut so = do_world(P, g, e, R, env_id, s, false, active0, true);
         ret += so.reward;
         done = s.time >= P.episode;                                            // core.py:438
         account_episode<true>(P, g.gl == 0 && t.live, e, so, s, done, auto_reset, acc4, acc_dirty);
@@ -242,11 +244,12 @@ __global__ void __launch_bounds__(BLOCK, (RC == 16 ? WH_MIN_BLOCKS_LARGE : RC ==
     if (g.gl == 0) acc4 = reinterpret_cast<const int4 *>(P.acc)[e];
     for (int it = 0; it < P.n_steps; ++it) {
         int act = -1;
-        if (GREEDY) act = greedy_from_state<GC, RC>(P, g, R, env_id, s);
+        unsigned long long active0 = 0ull;
+        if (GREEDY) act = greedy_from_state<GC, RC>(P, g, R, env_id, s, active0);
         else if (g.gl < R) act = acts[e * R + g.gl];
         s.time += 1;                                                           // core.py:267
         do_moves<GC, RC>(P, g, R, s.A, act, -1, false, s.pos16);
-        const StepOut so = do_world(P, g, e, R, env_id, s, false);
+        const StepOut so = do_world(P, g, e, R, env_id, s, false, active0, GREEDY);
         done = s.time >= P.episode;                                            // core.py:438
         if (per_step) {
             if (t.live && g.gl < R) rew[e * R + g.gl] = so.reward;              // core.py:435

@@ -528,7 +528,11 @@ struct StepOut {
 
 template <int GC>
 __device__ __forceinline__ StepOut do_world(const KParams &P, const Group<GC> &g, env_t e, int R,
-                                            uint32_t env_id, EnvRegs &s, bool replay) {
+                                            uint32_t env_id, EnvRegs &s, bool replay,
+                                            unsigned long long active_in = 0ull, bool have_active = false) {
+    // active_in / have_active: the active-request mask as it was BEFORE this step, when the caller already has
+    // it (the in-kernel solver computed it): the mask after expiry and pickups is then derived from it instead
+    // of being gathered from the lanes a second time.
     StepOut o;
     const Geo<GC> geo(P);
     // ---- core.py:303-306 expiry (before pickup detection) ----
@@ -536,6 +540,7 @@ __device__ __forceinline__ StepOut do_world(const KParams &P, const Group<GC> &g
     // -1 is added to the active halves with the packed 16-bit add (VIADD.16x2: no borrow between the
     // halves), and a half that reached 0 — found with the packed unsigned minimum — has expired.
     int nexp = 0;
+    bool expired_any;
     {
         const uint32_t inv = ~s.pt4;
         const uint32_t d0 = ((inv >> 7) & 1u) * 0xFFFFu + ((inv >> 15) & 1u) * 0xFFFF0000u;
@@ -543,7 +548,8 @@ __device__ __forceinline__ StepOut do_world(const KParams &P, const Group<GC> &g
         s.tmr.x = __vadd2(s.tmr.x, d0);
         s.tmr.y = __vadd2(s.tmr.y, d1);
         const bool any0 = (__vminu2(s.tmr.x, 0x00010001u) & __vminu2(s.tmr.y, 0x00010001u)) != 0x00010001u;
-        if (__any_sync(FULL, any0)) {               // rare: a request expires at most once per episode
+        expired_any = __any_sync(FULL, any0);
+        if (expired_any) {                          // rare: a request expires at most once per episode
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const uint32_t t = ((j < 2 ? s.tmr.x : s.tmr.y) >> (16 * (j & 1))) & 0xFFFFu;
@@ -562,17 +568,26 @@ __device__ __forceinline__ StepOut do_world(const KParams &P, const Group<GC> &g
     const bool picks = cand >= 0 && s.atgt == -1 && tg > -1;
     float reward = 0.0f;
     o.npick = 0;
-    if (__any_sync(FULL, picks)) {                  // rare: most env-steps see no pickup
-        const unsigned long long served = g.or64(picks ? (1ull << cand) : 0ull);
-        const uint32_t nib = (g.gl < 16) ? (uint32_t)((served >> (4 * g.gl)) & 0xFull) : 0u;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if ((nib >> j) & 1u) { s.pt4 |= 0xFFu << (8 * j); set_timer(s, j, 0xFFFFu); }  // core.py:330-331
+    unsigned long long served = 0ull;
+    if (__any_sync(FULL, picks)) {                  // rare with random actions, every other step with the greedy solver
+        // every group walks its own pickers (usually one); a picker's point belongs to lane cand / 4
+        const uint32_t pm = g.ballot(picks);
+        o.npick = __popc(pm);
+        for (uint32_t rem = pm; __any_sync(FULL, rem != 0u); rem &= rem - 1u) {
+            const int c = (int)g.shfl((uint32_t)cand, rem ? __ffs((int)rem) - 1 : 0);
+            if (rem != 0u) {
+                served |= 1ull << c;
+                if ((c >> 2) == g.gl) {                                         // core.py:330-331
+                    const int j = c & 3;
+                    s.pt4 |= 0xFFu << (8 * j);
+                    set_timer(s, j, 0xFFFFu);
+                }
+            }
+        }
         if (picks) { s.atgt = tg; reward = 1.0f; }                             // core.py:327-329,335
-        o.npick = __popc(g.ballot(picks));
     }
     // ---- core.py:338-351 respawn until exactly R requests are active ----
-    unsigned long long active = active_mask(g, s.pt4);
+    unsigned long long active = (have_active && !expired_any) ? (active_in & ~served) : active_mask(g, s.pt4);
     int sp = -1, st_ = -1, k;
     uint32_t up = 0, ut = 0;
     if (replay) {
@@ -1219,9 +1234,10 @@ __device__ __forceinline__ unsigned long long do_reset(const KParams &P, const G
 // agent to its delivery cell.
 template <int GC, int RC>
 __device__ __forceinline__ int greedy_from_state(const KParams &P, const Group<GC> &g, int R,
-                                                 uint32_t env_id, const EnvRegs &s) {
+                                                 uint32_t env_id, const EnvRegs &s, unsigned long long &active_out) {
     const Geo<GC> geo(P);
     const unsigned long long active = active_mask(g, s.pt4);
+    active_out = active;                             // do_world derives the post-step mask from it
     const int px = s.pos16 & 0xFF, py = s.pos16 >> 8;
     // lane r takes the r-th active pickup point's cell
     const int nact = __popcll(active);
