@@ -950,14 +950,26 @@ static bool device_can_address(const void *p, void **dev_ptr) {
     return true;
 }
 
+// all eight observation tensors of n envs, device -> host, on stream s
+static int obs_to_host(const wh_obs &ob, const wh_obs &oh, int64_t n, int64_t R, cudaStream_t s) {
+    CK(cudaMemcpyAsync(oh.num_agents, ob.num_agents, n * R * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(oh.self_position, ob.self_position, n * R * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(oh.self_availability, ob.self_availability, n * R, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(oh.self_delivery_target, ob.self_delivery_target, n * R * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(oh.other_positions, ob.other_positions, n * R * (R - 1) * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(oh.other_availabilities, ob.other_availabilities, n * R * (R - 1), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(oh.other_delivery_targets, ob.other_delivery_targets, n * R * (R - 1) * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(oh.requests, ob.requests, n * R * R * 16, cudaMemcpyDeviceToHost, s));
+    return 0;
+}
+
 static int env_step_issue(wh_env *E, const int32_t *actions, float *rewards, uint8_t *dones,
                          const wh_obs *obs_host, bool greedy, bool compact) {
     CK(cudaSetDevice(E->device));
     const int64_t R = E->R;
-    // Direct modes: the step kernel itself moves the step's I/O over PCIe — it writes rewards and dones
-    // straight into the caller's page-locked buffers (and, mode 1, reads the actions from them), so there is
-    // no separate copy to wait for before / after the kernel. Falls back to the copy pipeline when a buffer
-    // is not page-locked.
+    // Direct mode: the step kernel itself moves the step's I/O over PCIe — it reads the actions from and writes
+    // the rewards into the caller's page-locked buffers, so there is no separate copy to wait for before / after
+    // the kernel. Falls back to the copy pipeline when a buffer is not page-locked.
     void *d_act = nullptr, *d_rew = nullptr;
     if (E->direct && device_can_address(rewards, &d_rew) && (greedy || device_can_address(actions, &d_act))) {
         cudaStream_t s = E->streams[0];
@@ -974,17 +986,7 @@ static int env_step_issue(wh_env *E, const int32_t *actions, float *rewards, uin
         E->launches += 1;
         if (rc) return rc;
         CK(cudaMemcpyAsync(dones, E->d_dones, (size_t)E->N, cudaMemcpyDeviceToHost, s));
-        if (obs_host) {
-            const wh_obs &ob = E->obs; const wh_obs &oh = *obs_host; const int64_t n = E->N;
-            CK(cudaMemcpyAsync(oh.num_agents, ob.num_agents, n * R * 4, cudaMemcpyDeviceToHost, s));
-            CK(cudaMemcpyAsync(oh.self_position, ob.self_position, n * R * 8, cudaMemcpyDeviceToHost, s));
-            CK(cudaMemcpyAsync(oh.self_availability, ob.self_availability, n * R, cudaMemcpyDeviceToHost, s));
-            CK(cudaMemcpyAsync(oh.self_delivery_target, ob.self_delivery_target, n * R * 8, cudaMemcpyDeviceToHost, s));
-            CK(cudaMemcpyAsync(oh.other_positions, ob.other_positions, n * R * (R - 1) * 8, cudaMemcpyDeviceToHost, s));
-            CK(cudaMemcpyAsync(oh.other_availabilities, ob.other_availabilities, n * R * (R - 1), cudaMemcpyDeviceToHost, s));
-            CK(cudaMemcpyAsync(oh.other_delivery_targets, ob.other_delivery_targets, n * R * (R - 1) * 8, cudaMemcpyDeviceToHost, s));
-            CK(cudaMemcpyAsync(oh.requests, ob.requests, n * R * R * 16, cudaMemcpyDeviceToHost, s));
-        }
+        if (obs_host) return obs_to_host(E->obs, *obs_host, E->N, R, s);
         return 0;
     }
     for (int c = 0; c < E->n_chunks; ++c) {
@@ -1020,17 +1022,8 @@ static int env_step_issue(wh_env *E, const int32_t *actions, float *rewards, uin
         else
             CK(cudaMemcpyAsync(rewards + e0 * R, E->d_rewards + e0 * R, n * R * 4, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(dones + e0, E->d_dones + e0, n, cudaMemcpyDeviceToHost, s));
-        if (obs_host) {
-            const wh_obs oh = offset_obs(*obs_host, e0, R);
-            CK(cudaMemcpyAsync(oh.num_agents, ob.num_agents, n * R * 4, cudaMemcpyDeviceToHost, s));
-            CK(cudaMemcpyAsync(oh.self_position, ob.self_position, n * R * 8, cudaMemcpyDeviceToHost, s));
-            CK(cudaMemcpyAsync(oh.self_availability, ob.self_availability, n * R, cudaMemcpyDeviceToHost, s));
-            CK(cudaMemcpyAsync(oh.self_delivery_target, ob.self_delivery_target, n * R * 8, cudaMemcpyDeviceToHost, s));
-            CK(cudaMemcpyAsync(oh.other_positions, ob.other_positions, n * R * (R - 1) * 8, cudaMemcpyDeviceToHost, s));
-            CK(cudaMemcpyAsync(oh.other_availabilities, ob.other_availabilities, n * R * (R - 1), cudaMemcpyDeviceToHost, s));
-            CK(cudaMemcpyAsync(oh.other_delivery_targets, ob.other_delivery_targets, n * R * (R - 1) * 8, cudaMemcpyDeviceToHost, s));
-            CK(cudaMemcpyAsync(oh.requests, ob.requests, n * R * R * 16, cudaMemcpyDeviceToHost, s));
-        }
+        if (obs_host)
+            if (int rc2 = obs_to_host(ob, offset_obs(*obs_host, e0, R), n, R, s)) return rc2;
     }
     return 0;
 }
