@@ -102,6 +102,12 @@ typedef struct wh_prev {
 #define WH_FLAG_PER_STEP_OUT 8  /* wh_multi_step: rewards / dones / observations are [T, N, ...] tensors and step t
                                   writes slice t (otherwise: reward sums, last dones, observations overwritten) */
 
+/* wh_multi_step picks its kernel from the launch size; bits 4-6 of `flags` force one (tests, tuning):
+ * 0 = automatic, 1 = throughput kernel (256-thread blocks, register-capped), 2 = the same with 64-thread blocks and
+ * no register cap, 3 / 4 = warp-specialised kernel with 1 / 2 observation warps per env tile (needs obs and one of
+ * the reference variants' geometries, else WH_E_ARG) */
+#define WH_FLAG_MULTI_KERNEL(k) (((k) & 7) << 4)
+
 /* stats vector (unsigned 64-bit counters, device memory, WH_NUM_STATS entries):
  * [0] episodes [1] return_sum [2] pickups [3] deliveries [4] expired [5..7] reserved
  * [8+2(n-1)] episodes with n agents, [9+2(n-1)] their return sum  (scripts/train.py:18-23) */
@@ -182,7 +188,7 @@ int wh_greedy_rollout(const wh_config *cfg, const wh_state *st, int64_t n_envs, 
  * open-loop replays (recorded / random action tensors, the greedy baseline).
  *   actions  int32 [n_steps, N, R] open-loop actions (-1 = absent), or NULL = the in-kernel greedy solver
  *            (solvers.py:27-58; solver_seed / rand_threshold as in wh_greedy_step);
- *   flags    WH_FLAG_AUTO_RESET, WH_FLAG_PER_STEP_OUT;
+ *   flags    WH_FLAG_AUTO_RESET, WH_FLAG_PER_STEP_OUT, WH_FLAG_MULTI_KERNEL(k);
  *   rewards  f32 [n_steps,N,R] / dones u8 [n_steps,N] with WH_FLAG_PER_STEP_OUT, else [N,R] per-agent
  *            reward SUMS over the steps and [N] the last step's dones;
  *   obs      NULL = no observations; otherwise written EVERY step: into slice t of [n_steps,N,...] tensors

@@ -13,6 +13,12 @@ FLAG_AUTO_RESET = 1
 FLAG_COMPACT_IO = 2
 FLAG_NO_PDL = 4
 FLAG_PER_STEP_OUT = 8
+# wh_multi_step kernel selection (WH_FLAG_MULTI_KERNEL(k), bits 4-6 of flags)
+MULTI_KERNELS = {"auto": 0, "throughput": 1, "low_occupancy": 2, "ws1": 3, "ws2": 4}
+
+
+def flag_multi_kernel(name):
+    return (MULTI_KERNELS[name or "auto"] & 7) << 4
 
 OBS_KEYS = (
     "num_agents", "self_position", "self_availability", "self_delivery_target",

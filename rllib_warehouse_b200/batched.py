@@ -301,7 +301,7 @@ class BatchedWarehouse:
         return self.rewards
 
     def multi_step(self, steps: int, actions=None, random_action_prob=0.0, solver_seed=0, with_obs=True,
-                   per_step=False, out=None):
+                   per_step=False, out=None, kernel=None):
         """`steps` consecutive `env.step` calls in ONE kernel launch (wh_multi_step); the state stays in
         registers between them. actions: int [steps, N, R] open-loop actions, or None = the in-kernel greedy
         solver (one run.py:42-62 iteration per step). Every step's observations are written (with_obs).
@@ -309,12 +309,14 @@ class BatchedWarehouse:
         per_step=False: observations land in the resident tensors (each step overwrites the previous one,
         exactly what `steps` single launches leave behind); returns (obs, reward SUMS [N,R], last dones [N]).
         per_step=True: returns per-step tensors — obs dict of [steps, N, ...], rewards [steps, N, R],
-        dones [steps, N] (allocated here, or pass `out=(obs_dict, rewards, dones)` to reuse buffers)."""
+        dones [steps, N] (allocated here, or pass `out=(obs_dict, rewards, dones)` to reuse buffers).
+        kernel: None / "auto" = chosen from the launch size; "throughput", "low_occupancy", "ws1", "ws2" force one
+        (WH_FLAG_MULTI_KERNEL; all produce identical results)."""
         dev, N, R, T = self.device, self.N, self.R, int(steps)
         if actions is not None:
             actions = _dev_tensor(actions, torch.int32, dev, (T, N, R))
         thr = int(float(random_action_prob) * 4294967296.0)
-        flags = nv.FLAG_AUTO_RESET if self.auto_reset else 0
+        flags = (nv.FLAG_AUTO_RESET if self.auto_reset else 0) | nv.flag_multi_kernel(kernel)
         if per_step:
             flags |= nv.FLAG_PER_STEP_OUT
             if out is None:

@@ -36,6 +36,12 @@ namespace wh {
 #ifndef WH_LARGE_DYN_SMEM
 #define WH_LARGE_DYN_SMEM 24576   // 34.5 KB static + 24 KB: 3 blocks fit in 227 KB, 4 do not
 #endif
+#ifndef WH_MULTI_WS_DEFAULT
+#define WH_MULTI_WS_DEFAULT 2           // observation warps per env tile of k_multi_ws (0 = never use it)
+#endif
+#ifndef WH_MULTI_WS_MAX_TILES_PER_SM
+#define WH_MULTI_WS_MAX_TILES_PER_SM 8  // k_multi_ws while the launch has fewer env tiles per SM than this
+#endif
 constexpr int BLOCK = WH_BLOCK;   // threads per block (tuning: -DWH_BLOCK / -DWH_MIN_BLOCKS)
 
 // ---------------------------------------------------------------------------------------------
@@ -46,8 +52,10 @@ template <int GC>
 struct Tile {
     env_t e, env0;   // this lane's environment; the first environment of the warp
     bool live;
-    __device__ __forceinline__ Tile(const KParams &P, const Group<GC> &g) {
-        const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // blockDim.x <= BLOCK
+    __device__ __forceinline__ Tile(const KParams &P, const Group<GC> &g)
+        : Tile(P, g, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) {}                 // blockDim.x <= BLOCK
+    // warp = index of the env tile (k_multi_ws: all warps of a block work on the block's one tile)
+    __device__ __forceinline__ Tile(const KParams &P, const Group<GC> &g, uint32_t warp) {
         env0 = warp * (uint32_t)g.epw;
         const uint32_t env = env0 + (uint32_t)g.gi, n = (uint32_t)P.N;
         live = !g.ghost && env < n;
@@ -219,8 +227,10 @@ __global__ void __launch_bounds__(BLOCK, (RC == 16 ? 4 : WH_MIN_BLOCKS)) k_rollo
 // resident [N,...] tensors. Actions: open-loop int32 [T,N,R], or the in-kernel greedy solver. Envs are
 // warp-private, so the steps of different warps drift apart freely: no per-step launch ramp / tail, which
 // is what bounds launch-sized batches (BASELINE configs[1]: 4 096 Small envs, configs[2]: 65 536 Medium).
-template <int GC, int RC, bool GREEDY>
-__global__ void __launch_bounds__(BLOCK, (RC == 16 ? WH_MIN_BLOCKS_LARGE : RC == 9 ? WH_MIN_BLOCKS_MEDIUM : RC == 4 ? WH_MIN_BLOCKS_SMALL : WH_MIN_BLOCKS)) k_multi(const __grid_constant__ KParams P) {
+// LOWOCC: the instantiation for launch-sized batches (64-thread blocks spread over the SMs): no register cap —
+// occupancy is irrelevant there and the capped kernel spills (Small: 232 B at 40 registers).
+template <int GC, int RC, bool GREEDY, bool LOWOCC = false>
+__global__ void __launch_bounds__(LOWOCC ? 64 : BLOCK, LOWOCC ? 1 : (RC == 16 ? WH_MIN_BLOCKS_LARGE : RC == 9 ? WH_MIN_BLOCKS_MEDIUM : RC == 4 ? WH_MIN_BLOCKS_SMALL : WH_MIN_BLOCKS)) k_multi(const __grid_constant__ KParams P) {
     __shared__ __align__(16) unsigned char smem[StageMem<GC, RC>::BYTES];
     const Group<GC> g(P.G);
     const Tile<GC> t(P, g);
@@ -281,6 +291,148 @@ __global__ void __launch_bounds__(BLOCK, (RC == 16 ? WH_MIN_BLOCKS_LARGE : RC ==
     }
     if (t.live) {
         store_env(P, g, e, R, (RC ? 4 * GC : P.P), s, true);
+        if (acc_dirty) reinterpret_cast<int4 *>(P.acc)[e] = acc4;
+        if (!per_step) {
+            if (g.gl < R) P.rewards[e * R + g.gl] = ret;
+            if (g.gl == 0) P.dones[e] = done ? 1 : 0;
+        }
+    }
+}
+
+// k_multi for LAUNCH-SIZED batches (fewer env tiles than the GPU has warp schedulers; BASELINE configs[1]:
+// 4 096 Small envs = 512 tiles on 592 schedulers). There a step is one ~1 000-instruction dependent chain per
+// warp at a single-warp IPC of ~0.2 (profiles/r02_ncu_multi_small4096.txt), and most schedulers idle. The
+// loop-carried part of that chain is only solver -> moves -> world; the observation of step t hangs off it.
+// So a block = one env tile worked on by 1 + NOBS warps: warp 0 runs the step logic and hands the post-step
+// state of every lane (one 16-byte word: cell, delivery target, agent count, observation flavour, the
+// lane's four pickup targets, the active-request mask) to the observation warp(s) through a two-deep
+// shared-memory ring guarded by named barriers (bar.arrive / bar.sync: full[2], empty[2]); the observation
+// warps build and store step t's observation while warp 0 is already in step t+1. With NOBS = 2 the keys are
+// split (build_obs PART 1: num_agents / self_* / requests, PART 2: other_*). No register cap: occupancy is
+// irrelevant in this regime, and the capped k_multi spills (Small: 232 B at 40 registers).
+// Outputs are bit-identical to k_multi (same device functions, same order of stores per address).
+// barrier ids are immediates (two ring slots -> ids 1,2 = full, 3,4 = empty), so ptxas reserves 5 barriers, not 16
+template <int ID>
+__device__ __forceinline__ void named_bar_sync_i(int n) { asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(n) : "memory"); }
+template <int ID>
+__device__ __forceinline__ void named_bar_arrive_i(int n) { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "r"(n) : "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int n) {
+    if (id == 1) named_bar_sync_i<1>(n); else if (id == 2) named_bar_sync_i<2>(n); else if (id == 3) named_bar_sync_i<3>(n); else named_bar_sync_i<4>(n);
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int n) {
+    if (id == 1) named_bar_arrive_i<1>(n); else if (id == 2) named_bar_arrive_i<2>(n); else if (id == 3) named_bar_arrive_i<3>(n); else named_bar_arrive_i<4>(n);
+}
+// the arrive that frees a ring slot: `dep` = a value loaded from the slot, so the load has completed
+__device__ __forceinline__ void named_bar_arrive_after(int id, int n, uint32_t dep) {
+    asm volatile("{\n\t.reg .b32 t;\n\tmov.b32 t, %0;\n\t}" ::"r"(dep) : "memory");
+    named_bar_arrive(id, n);
+}
+
+template <int GC, int RC, int PART>
+__device__ __forceinline__ void multi_ws_obs_loop(const KParams &P, const Group<GC> &g, const Tile<GC> &t, const uint4 (*ring)[32],
+                                                  unsigned char *smem, int nthreads) {
+    constexpr int R = RC;
+    const env_t e = t.e;
+    const bool per_step = (P.flags & WH_FLAG_PER_STEP_OUT) != 0;
+    const size_t NR = (size_t)P.N * R;
+    wh_obs o = P.obs;
+    const int T = P.n_steps;
+    for (int it = 0; it < T; ++it) {
+        const int b = it & 1;
+        named_bar_sync(1 + b, nthreads);                                        // full[b]
+        const uint4 h = ring[b][g.lane];
+        if (it + 2 < T) named_bar_arrive_after(3 + b, nthreads, h.x ^ h.y ^ h.z ^ h.w);   // empty[b]
+        EnvRegs s;
+        s.pos16 = h.x & 0xFFFFu;
+        s.atgt = (int)(int8_t)((h.x >> 16) & 0xFFu);
+        s.A = (int)((h.x >> 24) & 0x3Fu);
+        const int flavour = (h.x >> 30) & 1u ? WH_OBS_RESET : WH_OBS_STEP;
+        s.pt4 = h.y;
+        s.tmr = make_uint2(0u, 0u); s.time = 0; s.ep = 0;                       // not read by build_obs
+        const unsigned long long active = (unsigned long long)h.z | ((unsigned long long)h.w << 32);
+        build_obs<GC, RC, PART>(P, o, g, e, R, s, active, target_cell16<GC>(P, s.atgt), flavour, t.live,
+                                StageMem<GC, RC>::mine(smem, g), StageMem<GC, RC>::warp_area(smem), t.env0);
+        __syncwarp();                                                           // staging is reused by the next step
+        if (per_step) {
+            o.num_agents += NR; o.self_position += 2 * NR; o.self_availability += NR; o.self_delivery_target += 2 * NR;
+            o.other_positions += 2 * NR * (R - 1); o.other_availabilities += NR * (R - 1);
+            o.other_delivery_targets += 2 * NR * (R - 1); o.requests += 4 * NR * R;
+        }
+    }
+}
+
+template <int GC, int RC, bool GREEDY, int NOBS>
+__global__ void __launch_bounds__(32 * (1 + NOBS)) k_multi_ws(const __grid_constant__ KParams P) {
+    static_assert(RC != 0 && (NOBS == 1 || NOBS == 2), "variant kernels only");
+    __shared__ __align__(16) unsigned char smem[StageMem<GC, RC>::BYTES / (BLOCK / 32) * (1 + NOBS)];
+    __shared__ __align__(16) uint4 ring[2][32];
+    constexpr int NT = 32 * (1 + NOBS);
+    constexpr int R = RC;
+    const int role = threadIdx.x >> 5;
+    const Group<GC> g(P.G);
+    const Tile<GC> t(P, g, blockIdx.x);
+    if (role != 0) {
+        if (NOBS == 1) multi_ws_obs_loop<GC, RC, 3>(P, g, t, ring, smem, NT);
+        else if (role == 1) multi_ws_obs_loop<GC, RC, 1>(P, g, t, ring, smem, NT);
+        else multi_ws_obs_loop<GC, RC, 2>(P, g, t, ring, smem, NT);
+        return;
+    }
+    const env_t e = t.e;
+    const uint32_t env_id = (uint32_t)P.env_id0 + e;
+    EnvRegs s;
+    load_env(P, g, e, R, 4 * GC, s);
+    const bool auto_reset = (P.flags & WH_FLAG_AUTO_RESET) != 0;
+    const bool per_step = (P.flags & WH_FLAG_PER_STEP_OUT) != 0;
+    const int32_t *acts = P.actions;
+    float *rew = P.rewards;
+    uint8_t *dn = P.dones;
+    const size_t NR = (size_t)P.N * R, N = (size_t)P.N;
+    float ret = 0.0f;
+    bool done = false;
+    int4 acc4 = make_int4(0, 0, 0, 0);
+    bool acc_dirty = false;
+    if (g.gl == 0) acc4 = reinterpret_cast<const int4 *>(P.acc)[e];
+    for (int it = 0; it < P.n_steps; ++it) {
+        int act = -1;
+        unsigned long long active0 = 0ull;
+        if (GREEDY) act = greedy_from_state<GC, RC>(P, g, R, env_id, s, active0);
+        else if (g.gl < R) act = acts[e * R + g.gl];
+        s.time += 1;                                                           // core.py:267
+        do_moves<GC, RC>(P, g, R, s.A, act, -1, false, s.pos16);
+        const StepOut so = do_world(P, g, e, R, env_id, s, false, active0, GREEDY);
+        done = s.time >= P.episode;                                            // core.py:438
+        unsigned long long active = so.active;
+        uint32_t flav = 0u;
+        // the hand-over comes first: everything after it is off the observation warps' critical path
+        const bool resets = auto_reset && __any_sync(FULL, done);
+        if (!resets) {
+            const int b = it & 1;
+            if (it >= 2) named_bar_sync(3 + b, NT);                             // empty[b]
+            ring[b][g.lane] = make_uint4((s.pos16 & 0xFFFFu) | (((uint32_t)s.atgt & 0xFFu) << 16) | ((uint32_t)s.A << 24),
+                                         s.pt4, (uint32_t)active, (uint32_t)(active >> 32));
+            named_bar_arrive(1 + b, NT);                                        // full[b]
+        }
+        if (per_step) {
+            if (t.live && g.gl < R) rew[e * R + g.gl] = so.reward;              // core.py:435
+            if (t.live && g.gl == 0) dn[e] = done ? 1 : 0;
+        } else {
+            ret += so.reward;
+        }
+        account_episode<true>(P, g.gl == 0 && t.live, e, so, s, done, auto_reset, acc4, acc_dirty);
+        if (resets) {
+            const unsigned long long a2 = do_reset(P, g, e, R, env_id, s, false, done && t.live);
+            if (done) { active = a2; flav = 1u; }
+            const int b = it & 1;
+            if (it >= 2) named_bar_sync(3 + b, NT);                             // empty[b]
+            ring[b][g.lane] = make_uint4((s.pos16 & 0xFFFFu) | (((uint32_t)s.atgt & 0xFFu) << 16) | ((uint32_t)s.A << 24) | (flav << 30),
+                                         s.pt4, (uint32_t)active, (uint32_t)(active >> 32));
+            named_bar_arrive(1 + b, NT);                                        // full[b]
+        }
+        if (!GREEDY) acts += NR;
+        if (per_step) { rew += NR; dn += N; }
+    }
+    if (t.live) {
+        store_env(P, g, e, R, 4 * GC, s, true);
         if (acc_dirty) reinterpret_cast<int4 *>(P.acc)[e] = acc4;
         if (!per_step) {
             if (g.gl < R) P.rewards[e * R + g.gl] = ret;
@@ -556,7 +708,20 @@ static void launch_kind(Kind kind, const KParams &K, cudaStream_t s) {
         // long dependent chain per warp, so extra warps only add instructions.)
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-        const unsigned threads = warps >= (long long)sms * 16 ? BLOCK : 64;
+        const int force = (K.flags >> 4) & 7;                // WH_FLAG_MULTI_KERNEL
+        if constexpr (RC != 0) {
+            // launch-sized batches that write observations: the warp-specialised kernel (see k_multi_ws);
+            // WH_B200_MULTI_WS = 0 (off) / 1 / 2 observation warps per env tile
+            static const int ws_default = [] { const char *v = getenv("WH_B200_MULTI_WS"); return v ? atoi(v) : WH_MULTI_WS_DEFAULT; }();
+            const int ws = force >= 3 ? force - 2 : force ? 0 : (K.obs.requests && warps < (long long)sms * WH_MULTI_WS_MAX_TILES_PER_SM) ? ws_default : 0;
+            if (ws > 0) {
+                const bool gr = kind == K_GMULTI;
+                if (ws == 1) { if (gr) k_multi_ws<GC, RC, true, 1><<<(unsigned)warps, 64, 0, s>>>(K); else k_multi_ws<GC, RC, false, 1><<<(unsigned)warps, 64, 0, s>>>(K); }
+                else { if (gr) k_multi_ws<GC, RC, true, 2><<<(unsigned)warps, 96, 0, s>>>(K); else k_multi_ws<GC, RC, false, 2><<<(unsigned)warps, 96, 0, s>>>(K); }
+                break;
+            }
+        }
+        const unsigned threads = force == 1 ? BLOCK : force == 2 ? 64 : warps >= (long long)sms * 16 ? BLOCK : 64;
         const unsigned mgrid = (unsigned)((warps * 32 + threads - 1) / threads);
         if (dyn) {
             static std::atomic<bool> once[2];
@@ -565,7 +730,10 @@ static void launch_kind(Kind kind, const KParams &K, cudaStream_t s) {
                 cudaFuncSetAttribute(k_multi<GC, RC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
             }
         }
-        if (kind == K_GMULTI) k_multi<GC, RC, true><<<mgrid, threads, dyn, s>>>(K);
+        if (threads == 64) {
+            if (kind == K_GMULTI) k_multi<GC, RC, true, true><<<mgrid, threads, 0, s>>>(K);
+            else k_multi<GC, RC, false, true><<<mgrid, threads, 0, s>>>(K);
+        } else if (kind == K_GMULTI) k_multi<GC, RC, true><<<mgrid, threads, dyn, s>>>(K);
         else k_multi<GC, RC, false><<<mgrid, threads, dyn, s>>>(K);
         break;
     }
@@ -743,7 +911,9 @@ int wh_multi_step(const wh_config *cfg, const wh_state *st, int64_t n_envs, int6
     if (int rc = fill_params(cfg, K, sh)) return rc;
     if (n_envs == 0 || n_steps == 0) return 0;
     if (!state_ok(st) || !rewards || !dones || n_steps < 0 || (obs && !obs_ok(obs))) return WH_E_ARG;
-    if (flags & ~(WH_FLAG_AUTO_RESET | WH_FLAG_PER_STEP_OUT)) return WH_E_ARG;
+    if (flags & ~(WH_FLAG_AUTO_RESET | WH_FLAG_PER_STEP_OUT | WH_FLAG_MULTI_KERNEL(7))) return WH_E_ARG;
+    const int force = (flags >> 4) & 7;
+    if (force > 4 || (force >= 3 && (!obs || sh.RC == 0))) return WH_E_ARG;
     set_state(K, st);
     if (obs) K.obs = *obs;
     K.N = n_envs; K.env_id0 = env_id0; K.seed = seed; K.solver_seed = solver_seed;

@@ -669,7 +669,9 @@ struct ObsStage {
     static constexpr int BYTES = COOP ? ((POS_BYTES + AV_BYTES + REQ_BYTES + 15) / 16) * 16 : RAW;
 };
 
-template <int GC, int RC>
+// PART: which keys this caller writes — bit 0: num_agents, self_*, requests; bit 1: other_* (k_multi_ws splits
+// one environment's observation between two warps; everybody else writes all of it)
+template <int GC, int RC, int PART = 3>
 __device__ __forceinline__ void build_obs(const KParams &P, const wh_obs &o, const Group<GC> &g, env_t e, int R,
                                           const EnvRegs &s, unsigned long long active, uint32_t tpos16,
                                           int flavour, bool live, unsigned char *stage,
@@ -695,19 +697,21 @@ __device__ __forceinline__ void build_obs(const KParams &P, const wh_obs &o, con
     const int my_a = (mine >> 28) & 1, nx_a = (next >> 28) & 1;
 
     // core.py:409-418 request list: active pickup points in ascending index, [px,py,dx,dy]
-    const bool have = g.gl < R && g.gl < __popcll(active);
-    const int p = ((RC != 0 && RC <= 4) ? nth_set_small<(RC ? RC : 1)>((uint32_t)active, have ? g.gl : 0)
-                                        : nth_set64<Group<GC>::PBITS>(active, have ? g.gl : 0)) & 63;
-    const uint32_t w4 = g.shfl(s.pt4, p >> 2);
     int4 rq = make_int4(null_pos, null_pos, null_pos, null_pos);  // only if < R active (unreachable)
-    if (have) {
-        const uint32_t pc = pickup_cell16(P, geo, p);
-        const uint32_t dc = delivery_cell16((int)((w4 >> (8 * (p & 3))) & 0x3Fu), geo.dim);
-        rq = make_int4(pc & 0xFF, pc >> 8, dc & 0xFF, dc >> 8);
+    if constexpr ((PART & 1) != 0) {
+        const bool have = g.gl < R && g.gl < __popcll(active);
+        const int p = ((RC != 0 && RC <= 4) ? nth_set_small<(RC ? RC : 1)>((uint32_t)active, have ? g.gl : 0)
+                                            : nth_set64<Group<GC>::PBITS>(active, have ? g.gl : 0)) & 63;
+        const uint32_t w4 = g.shfl(s.pt4, p >> 2);
+        if (have) {
+            const uint32_t pc = pickup_cell16(P, geo, p);
+            const uint32_t dc = delivery_cell16((int)((w4 >> (8 * (p & 3))) & 0x3Fu), geo.dim);
+            rq = make_int4(pc & 0xFF, pc >> 8, dc & 0xFF, dc >> 8);
+        }
     }
 
     const uint32_t row0 = e * (uint32_t)R;
-    if (live && g.gl < R) {
+    if ((PART & 1) != 0 && live && g.gl < R) {
         o.num_agents[row0 + g.gl] = s.A;
         reinterpret_cast<int2 *>(o.self_position)[row0 + g.gl] = my_p;
         o.self_availability[row0 + g.gl] = (int8_t)my_a;
@@ -737,10 +741,10 @@ __device__ __forceinline__ void build_obs(const KParams &P, const wh_obs &o, con
         // leaves alone, keep their observations): bit k = environment env0 + k
         const uint32_t lm = __ballot_sync(FULL, live);
         auto env_live = [&](int env) { return ((lm >> (env * GC)) & 1u) != 0u; };
-        if (!g.ghost && g.gl < RC) w_req[gi * RC + g.gl] = rq;                              // core.py:409-418
+        if ((PART & 1) != 0 && !g.ghost && g.gl < RC) w_req[gi * RC + g.gl] = rq;           // core.py:409-418
 #pragma unroll
         for (int a = 0; a < RC; ++a) {
-            if (writer) {
+            if ((PART & 2) != 0 && writer) {
                 const bool sh = g.gl >= a;                                      // core.py:426-427
                 w_pos[gi * St::ROWS + a * (RC - 1) + g.gl] = sh ? nx_p : my_p;
                 w_av[gi * St::ROWS + a * (RC - 1) + g.gl] = (int8_t)(sh ? nx_a : my_a);
@@ -748,7 +752,7 @@ __device__ __forceinline__ void build_obs(const KParams &P, const wh_obs &o, con
         }
         __syncwarp();
         const int lane = g.lane;
-        {   // requests [N,R,R,4]: R copies of the env's R request rows (core.py:429)
+        if constexpr ((PART & 1) != 0) {   // requests [N,R,R,4]: R copies of the env's R request rows (core.py:429)
             constexpr int PER_ENV = RC * RC;                                    // int4 per env
             const uint32_t base4 = env0 * (uint32_t)PER_ENV;
             const int mis = (int)(base4 & 1u);                                  // tile starts mid-sector
@@ -764,6 +768,7 @@ __device__ __forceinline__ void build_obs(const KParams &P, const wh_obs &o, con
                 }
             }
         }
+        if constexpr ((PART & 2) == 0) return;
         {   // other_positions [N,R,R-1,2]
             int4 *d = reinterpret_cast<int4 *>(o.other_positions) + env0 * (uint32_t)ROWS4;
 #pragma unroll
@@ -821,13 +826,14 @@ __device__ __forceinline__ void build_obs(const KParams &P, const wh_obs &o, con
         const bool writer = !g.ghost && g.gl < RC - 1;   // ghost lanes shadow group 0: keep them off its stage
 #pragma unroll
         for (int a = 0; a < RC; ++a) {
-            if (live && g.gl < RC) WH_ST(orq + a * RC, rq);                    // core.py:429
-            if (writer) {
+            if ((PART & 1) != 0 && live && g.gl < RC) WH_ST(orq + a * RC, rq);  // core.py:429
+            if ((PART & 2) != 0 && writer) {
                 const bool sh = g.gl >= a;                                      // core.py:426-427
                 s_pos[a * (RC - 1) + g.gl] = sh ? nx_p : my_p;
                 s_av[a * (RC - 1) + g.gl] = (int8_t)(sh ? nx_a : my_a);
             }
         }
+        if constexpr ((PART & 2) == 0) return;
         __syncwarp();
         if (live) {
 #pragma unroll
@@ -878,13 +884,13 @@ __device__ __forceinline__ void build_obs(const KParams &P, const wh_obs &o, con
     int2 *ot = reinterpret_cast<int2 *>(o.other_delivery_targets) + row0 * (R - 1) + g.gl;
     int8_t *oa = o.other_availabilities + row0 * (R - 1) + g.gl;
     for (int a = 0; a < RR; ++a) {
-        if (g.gl < R - 1) {
+        if ((PART & 2) != 0 && g.gl < R - 1) {
             const bool sh = g.gl >= a;                                          // core.py:426-427
             WH_ST(op + a * (R - 1), sh ? nx_p : my_p);
             WH_ST(oa + a * (R - 1), (int8_t)(sh ? nx_a : my_a));
             WH_ST(ot + a * (R - 1), flavour == WH_OBS_STEP ? t_fixed : (sh ? nx_t : my_t));
         }
-        if (g.gl < R) WH_ST(orq + a * R, rq);                                  // core.py:429
+        if ((PART & 1) != 0 && g.gl < R) WH_ST(orq + a * R, rq);               // core.py:429
     }
 }
 

@@ -585,8 +585,12 @@ def test_multi_step_greedy_rollout_kernel(size, n, p):
         assert np.array_equal(one.stats.cpu().numpy(), cpu.stats)
 
 
+MULTI_KERNELS = ["throughput", "low_occupancy", "ws1", "ws2"]   # every wh_multi_step kernel (WH_FLAG_MULTI_KERNEL)
+
+
+@pytest.mark.parametrize("kernel", MULTI_KERNELS)
 @pytest.mark.parametrize("size,n,T", [("small", 4097, 205), ("medium", 1000, 60), ("large", 515, 40)])
-def test_multi_step_open_loop_actions_every_step_vs_oracle(size, n, T):
+def test_multi_step_open_loop_actions_every_step_vs_oracle(size, n, T, kernel):
     """wh_multi_step with an open-loop [T,N,R] action tensor and per-step outputs: ONE launch runs the whole
     BASELINE configs[1] episode (Small, 4 096(+1) envs, random actions incl. absent agents, T = 205 passes
     the step-200 mass expiry); every step's observations, rewards and dones — and the final state — are
@@ -595,7 +599,7 @@ def test_multi_step_open_loop_actions_every_step_vs_oracle(size, n, T):
     gpu.reset(); cpu.reset()
     rng = np.random.Generator(np.random.PCG64(17))
     actions = rng.integers(-1, 9, size=(T, n, cpu.R)).astype(np.int32)
-    obs, rew, dones = gpu.multi_step(T, actions=actions, per_step=True)
+    obs, rew, dones = gpu.multi_step(T, actions=actions, per_step=True, kernel=kernel)
     obs = {k: v.cpu().numpy() for k, v in obs.items()}
     rew, dones = rew.cpu().numpy(), dones.cpu().numpy()
     for t in range(T):
@@ -608,8 +612,9 @@ def test_multi_step_open_loop_actions_every_step_vs_oracle(size, n, T):
     assert np.array_equal(gpu.stats.cpu().numpy(), cpu.stats)
 
 
+@pytest.mark.parametrize("kernel", MULTI_KERNELS + ["auto"])
 @pytest.mark.parametrize("size,n,p", [("small", 4099, 0.0), ("medium", 1000, 0.25), ("large", 515, 0.1)])
-def test_multi_step_greedy_equals_single_launches(size, n, p):
+def test_multi_step_greedy_equals_single_launches(size, n, p, kernel):
     """wh_multi_step with the in-kernel greedy solver, auto-reset and observations written every step over
     the resident tensors == the same number of wh_greedy_step launches: state, last observations
     (reset-flavour for envs that just finished), last dones, per-agent reward sums, statistics — across two
@@ -624,7 +629,7 @@ def test_multi_step_greedy_equals_single_launches(size, n, p):
         for _ in range(chunk):
             _, r, _ = one.greedy_step(random_action_prob=p, solver_seed=5)
             total += r
-        _, sums, dones = many.multi_step(chunk, random_action_prob=p, solver_seed=5)
+        _, sums, dones = many.multi_step(chunk, random_action_prob=p, solver_seed=5, kernel=kernel)
         assert torch.equal(sums, total), chunk
         assert torch.equal(dones, one.dones), chunk
         for k in one.state:

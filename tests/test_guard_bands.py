@@ -45,7 +45,9 @@ def test_no_out_of_bounds_writes(n):
     rng = np.random.Generator(np.random.PCG64(n))
     cfgs = [VARIANTS["small"], VARIANTS["medium"], VARIANTS["large"].replace(random_num_agents=True),
             WarehouseConfig(6, 14, (3, 7, 11), 30, 10, 6), WarehouseConfig(20, 20, (4, 8, 12, 16), 30, 10, 17)]
-    for cfg in cfgs:
+    for ci, cfg in enumerate(cfgs):
+        # the warp-specialised wh_multi_step kernels exist for the reference variants' geometries only
+        kerns = ("throughput", "low_occupancy") + (("ws1", "ws2") if ci < 3 else ())
         env = BatchedWarehouse(cfg, n, seed=7, auto_reset=True)
         arenas = rehome(env)
         env.reset()
@@ -59,8 +61,9 @@ def test_no_out_of_bounds_writes(n):
             env.step_flat(a)
             env.build_obs(t % 2)
             if t % 8 == 0:
-                env.multi_step(3)                                          # greedy, observations every step
-                env.multi_step(2, actions=rng.integers(-1, 9, size=(2, n, env.R)).astype(np.int32))
+                for kern in kerns:
+                    env.multi_step(3, kernel=kern)                             # greedy, observations every step
+                    env.multi_step(2, actions=rng.integers(-1, 9, size=(2, n, env.R)).astype(np.int32), kernel=kern)
         env.reset(env_mask=(rng.random(n) < 0.5).astype(np.uint8))
         torch.cuda.synchronize()
         assert guards_intact(arenas), cfg

@@ -1,20 +1,41 @@
 #!/usr/bin/env python
-"""BASELINE configs[1] shape in one launch: wh_multi_step on 4 096 Small envs (greedy, 200 steps per launch,
-observations written every step). `python tools/multi_small.py [envs] [steps]`; used under ncu to see what
-bounds the launch-sized regime."""
-import os, sys
+"""BASELINE configs[1] shape in one launch: wh_multi_step on 4 096 Small envs (200 steps per launch, observations
+written every step), every wh_multi_step kernel side by side (WH_FLAG_MULTI_KERNEL).
+`python tools/multi_small.py [variant] [envs] [steps] [kernel ...]`; with one kernel name it is the command line
+for ncu (what bounds the launch-sized regime)."""
+import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from rllib_warehouse_b200 import BatchedWarehouse, VARIANTS
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-T = int(sys.argv[2]) if len(sys.argv) > 2 else 200
-env = BatchedWarehouse(VARIANTS["small"], n, seed=1, auto_reset=True)
-env.reset()
-for _ in range(3):
-    env.multi_step(T)
-a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-torch.cuda.synchronize(); a.record()
-for _ in range(5):
-    env.multi_step(T)
-b.record(); torch.cuda.synchronize()
-print(f"{n} small envs: {a.elapsed_time(b) / 5 / T * 1e3:.3f} us per step")
+
+variant = sys.argv[1] if len(sys.argv) > 1 else "small"
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+T = int(sys.argv[3]) if len(sys.argv) > 3 else 200
+kernels = sys.argv[4:] or ["throughput", "low_occupancy", "ws1", "ws2", "auto"]
+cfg = VARIANTS[variant]
+R = cfg.num_requests
+alg = {"small": 711, "medium": 3071, "large": 9147}[variant] * n            # algorithmic bytes per step
+
+
+def timed(fn, reps=5):
+    for _ in range(2):
+        fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); a.record()
+    for _ in range(reps):
+        fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps / T * 1e3                                  # us per step
+
+
+for k in kernels:
+    env = BatchedWarehouse(cfg, n, seed=1, auto_reset=True)
+    env.reset()
+    us_g = timed(lambda: env.multi_step(T, kernel=k))
+    acts = torch.randint(0, 9, (T, n, R), dtype=torch.int32, device="cuda")
+    outs = env.multi_step(T, actions=acts, per_step=True, kernel=k)
+    us_o = timed(lambda: env.multi_step(T, actions=acts, per_step=True, out=outs, kernel=k))
+    print(json.dumps({"variant": variant, "envs": n, "steps_per_launch": T, "kernel": k,
+                      "greedy_us_per_step": round(us_g, 3), "greedy_frac_of_hbm_peak": round(alg / (us_g * 1e-6) / 6545.6e9, 4),
+                      "open_loop_per_step_out_us_per_step": round(us_o, 3),
+                      "open_loop_frac_of_hbm_peak": round(alg / (us_o * 1e-6) / 6545.6e9, 4)}), flush=True)
