@@ -534,6 +534,13 @@ def extras(args, dev, peak):
         ms_flat = _time_steps(lambda i: env.step_flat(rnd), steps, warm)
         ms_roll = _time_steps(lambda i: env.greedy_rollout(50, with_obs=False), 6, 2) / 50
         ms_multi = _time_steps(lambda i: env.multi_step(50), 6, 2) / 50
+        # the same with every step's outputs in their own [T,N,...] slice: nothing is overwritten, so every byte
+        # streams to HBM (T bounded so that the slices stay below ~16 GB)
+        fb_ = ALG_BYTES_PER_ENV_STEP[variant] * n
+        T_ps = max(2, min(50, int(16e9 // fb_)))
+        outs_ps = env.multi_step(T_ps, per_step=True)
+        ms_multi_ps = _time_steps(lambda i: env.multi_step(T_ps, per_step=True, out=outs_ps), 4, 1) / T_ps
+        del outs_ps
         sb = SOLVER_BYTES_PER_AGENT[variant] * n * A
         fb = ALG_BYTES_PER_ENV_STEP[variant] * n
         res[name] = {
@@ -550,7 +557,14 @@ def extras(args, dev, peak):
             # observations / rewards / dones written (same bytes per step as fused_greedy_step; no per-step
             # launch ramp / tail)
             "multi_step_greedy_obs_every_step": {"ms_per_step": ms_multi, "agent_steps_per_sec": n * A / (ms_multi * 1e-3),
-                                                 "frac": fb / ms_multi / 1e6 / peak, "steps_per_launch": 50},
+                                                 "frac": fb / ms_multi / 1e6 / peak, "steps_per_launch": 50,
+                                                 "note": "observations overwrite the resident tensors: consecutive steps' "
+                                                         "writes can merge in L2, so frac is a rate on the algorithmic "
+                                                         "bytes, not an HBM fraction"},
+            "multi_step_greedy_per_step_slices": {"ms_per_step": ms_multi_ps, "agent_steps_per_sec": n * A / (ms_multi_ps * 1e-3),
+                                                  "frac": fb / ms_multi_ps / 1e6 / peak, "steps_per_launch": T_ps,
+                                                  "note": "every step writes its own [t] slice of [T,N,...] tensors: all "
+                                                          "bytes stream to HBM; frac is an HBM roofline fraction"},
             # RLlib-flattened float32 observations from the step kernel: 4(9R+1) B/agent instead of 33R+4
             "step_flat_f32_obs": {"ms": ms_flat, "agent_steps_per_sec": n * A / (ms_flat * 1e-3),
                                   "alg_bytes_per_launch": fb + n * A * (4 * (9 * A + 1) - (33 * A + 4)),
@@ -613,12 +627,15 @@ def extras(args, dev, peak):
         "multi_step_greedy_200_steps_per_launch": {
             "ms_per_step": ms_multi, "agent_steps_per_sec": 4096 * 4 / (ms_multi * 1e-3),
             "frac": small_bytes / ms_multi / 1e6 / peak,
+            "kernel": "k_multi_ws: per env tile one step-logic warp + two observation warps (shared-memory ring, named barriers)",
             "note": "fraction of the HBM copy peak on the algorithmic bytes; the 2.9 MB working set is L2-resident "
                     "(observations overwrite the resident tensors), so the bound here is latency per step, not HBM"},
         "multi_step_open_loop_actions_per_step_outputs": {
             "ms_per_step": ms_multi_ol, "agent_steps_per_sec": 4096 * 4 / (ms_multi_ol * 1e-3),
             "frac": small_bytes / ms_multi_ol / 1e6 / peak,
-            "note": "random [200,N,R] action tensor in, [200,N,...] observations / rewards / dones out (446 MB per launch: streams to HBM)"},
+            "kernel": "k_multi_ws",
+            "note": "BASELINE configs[1] as stated (random actions): random [200,N,R] action tensor in, [200,N,...] "
+                    "observations / rewards / dones out (446 MB per launch: streams to HBM)"},
         "fused_greedy_step_eager": {"ms": ms_eager, "agent_steps_per_sec": 4096 * 4 / (ms_eager * 1e-3)},
         "fused_greedy_step_cuda_graph": {"ms": ms_graph, "agent_steps_per_sec": 4096 * 4 / (ms_graph * 1e-3),
                                          "frac": ALG_BYTES_PER_ENV_STEP["small"] * 4096 / ms_graph / 1e6 / peak,

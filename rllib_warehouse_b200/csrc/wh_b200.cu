@@ -42,6 +42,12 @@ namespace wh {
 #ifndef WH_MULTI_WS_MAX_TILES_PER_SM
 #define WH_MULTI_WS_MAX_TILES_PER_SM 8  // k_multi_ws while the launch has fewer env tiles per SM than this
 #endif
+#ifndef WH_WS_DIAG
+#define WH_WS_DIAG 0
+#endif
+#ifndef WH_MULTI_MIN_BLOCKS
+#define WH_MULTI_MIN_BLOCKS 3           // resident 256-thread blocks per SM of the throughput k_multi (80 registers: at 5 blocks = 48 registers it spilled 200 B and ran 14 % slower)
+#endif
 constexpr int BLOCK = WH_BLOCK;   // threads per block (tuning: -DWH_BLOCK / -DWH_MIN_BLOCKS)
 
 // ---------------------------------------------------------------------------------------------
@@ -230,7 +236,7 @@ __global__ void __launch_bounds__(BLOCK, (RC == 16 ? 4 : WH_MIN_BLOCKS)) k_rollo
 // LOWOCC: the instantiation for launch-sized batches (64-thread blocks spread over the SMs): no register cap —
 // occupancy is irrelevant there and the capped kernel spills (Small: 232 B at 40 registers).
 template <int GC, int RC, bool GREEDY, bool LOWOCC = false>
-__global__ void __launch_bounds__(LOWOCC ? 64 : BLOCK, LOWOCC ? 1 : (RC == 16 ? WH_MIN_BLOCKS_LARGE : RC == 9 ? WH_MIN_BLOCKS_MEDIUM : RC == 4 ? WH_MIN_BLOCKS_SMALL : WH_MIN_BLOCKS)) k_multi(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(LOWOCC ? 64 : BLOCK, LOWOCC ? 1 : (RC == 16 ? WH_MIN_BLOCKS_LARGE : WH_MULTI_MIN_BLOCKS)) k_multi(const __grid_constant__ KParams P) {
     __shared__ __align__(16) unsigned char smem[StageMem<GC, RC>::BYTES];
     const Group<GC> g(P.G);
     const Tile<GC> t(P, g);
@@ -252,11 +258,19 @@ __global__ void __launch_bounds__(LOWOCC ? 64 : BLOCK, LOWOCC ? 1 : (RC == 16 ? 
     int4 acc4 = make_int4(0, 0, 0, 0);
     bool acc_dirty = false;
     if (g.gl == 0) acc4 = reinterpret_cast<const int4 *>(P.acc)[e];
+    // open-loop actions: step t+1's action is loaded while step t runs (the load is the first thing on a
+    // step's dependent chain otherwise: an L2 / HBM round trip per step)
+    int act_next = -1;
+    if (!GREEDY && g.gl < R) act_next = acts[e * R + g.gl];
     for (int it = 0; it < P.n_steps; ++it) {
         int act = -1;
         unsigned long long active0 = 0ull;
         if (GREEDY) act = greedy_from_state<GC, RC>(P, g, R, env_id, s, active0);
-        else if (g.gl < R) act = acts[e * R + g.gl];
+        else {
+            act = act_next;
+            acts += NR;
+            if (it + 1 < P.n_steps && g.gl < R) act_next = acts[e * R + g.gl];
+        }
         s.time += 1;                                                           // core.py:267
         do_moves<GC, RC>(P, g, R, s.A, act, -1, false, s.pos16);
         const StepOut so = do_world(P, g, e, R, env_id, s, false, active0, GREEDY);
@@ -279,7 +293,6 @@ __global__ void __launch_bounds__(LOWOCC ? 64 : BLOCK, LOWOCC ? 1 : (RC == 16 ? 
                               StageMem<GC, RC>::warp_area(smem), t.env0);
             __syncwarp();                                                      // staging is reused by the next step
         }
-        if (!GREEDY) acts += NR;
         if (per_step) {
             rew += NR; dn += N;
             if (with_obs) {
@@ -350,9 +363,13 @@ __device__ __forceinline__ void multi_ws_obs_loop(const KParams &P, const Group<
         s.pt4 = h.y;
         s.tmr = make_uint2(0u, 0u); s.time = 0; s.ep = 0;                       // not read by build_obs
         const unsigned long long active = (unsigned long long)h.z | ((unsigned long long)h.w << 32);
+#if WH_WS_DIAG == 1   // tuning only: how fast is the logic warp alone?
+        if (s.pos16 == 0x12345u) o.num_agents[0] = (int)active + flavour;
+#else
         build_obs<GC, RC, PART>(P, o, g, e, R, s, active, target_cell16<GC>(P, s.atgt), flavour, t.live,
                                 StageMem<GC, RC>::mine(smem, g), StageMem<GC, RC>::warp_area(smem), t.env0);
         __syncwarp();                                                           // staging is reused by the next step
+#endif
         if (per_step) {
             o.num_agents += NR; o.self_position += 2 * NR; o.self_availability += NR; o.self_delivery_target += 2 * NR;
             o.other_positions += 2 * NR * (R - 1); o.other_availabilities += NR * (R - 1);
@@ -392,14 +409,27 @@ __global__ void __launch_bounds__(32 * (1 + NOBS)) k_multi_ws(const __grid_const
     int4 acc4 = make_int4(0, 0, 0, 0);
     bool acc_dirty = false;
     if (g.gl == 0) acc4 = reinterpret_cast<const int4 *>(P.acc)[e];
+    // open-loop actions: step t+1's action is loaded while step t runs (the load is the first thing on a
+    // step's dependent chain otherwise: an L2 / HBM round trip per step)
+    int act_next = -1;
+    if (!GREEDY && g.gl < R) act_next = acts[e * R + g.gl];
     for (int it = 0; it < P.n_steps; ++it) {
         int act = -1;
         unsigned long long active0 = 0ull;
         if (GREEDY) act = greedy_from_state<GC, RC>(P, g, R, env_id, s, active0);
-        else if (g.gl < R) act = acts[e * R + g.gl];
+        else {
+            act = act_next;
+            acts += NR;
+            if (it + 1 < P.n_steps && g.gl < R) act_next = acts[e * R + g.gl];
+        }
         s.time += 1;                                                           // core.py:267
+#if WH_WS_DIAG == 2   // tuning only: how fast are the observation warps alone?
+        StepOut so; so.reward = 0.f; so.active = active_mask(g, s.pt4); so.tpos16 = 0; so.npick = so.ndeliv = so.nexp = 0;
+        if (act == 12345) s.pos16 = 0;
+#else
         do_moves<GC, RC>(P, g, R, s.A, act, -1, false, s.pos16);
         const StepOut so = do_world(P, g, e, R, env_id, s, false, active0, GREEDY);
+#endif
         done = s.time >= P.episode;                                            // core.py:438
         unsigned long long active = so.active;
         uint32_t flav = 0u;
@@ -428,7 +458,6 @@ __global__ void __launch_bounds__(32 * (1 + NOBS)) k_multi_ws(const __grid_const
                                          s.pt4, (uint32_t)active, (uint32_t)(active >> 32));
             named_bar_arrive(1 + b, NT);                                        // full[b]
         }
-        if (!GREEDY) acts += NR;
         if (per_step) { rew += NR; dn += N; }
     }
     if (t.live) {

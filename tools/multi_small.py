@@ -31,11 +31,17 @@ def timed(fn, reps=5):
 for k in kernels:
     env = BatchedWarehouse(cfg, n, seed=1, auto_reset=True)
     env.reset()
-    us_g = timed(lambda: env.multi_step(T, kernel=k))
+    T_ps = max(2, min(T, int(16e9 // alg)))                                    # per-step slices stay below ~16 GB
     acts = torch.randint(0, 9, (T, n, R), dtype=torch.int32, device="cuda")
-    outs = env.multi_step(T, actions=acts, per_step=True, kernel=k)
-    us_o = timed(lambda: env.multi_step(T, actions=acts, per_step=True, out=outs, kernel=k))
-    print(json.dumps({"variant": variant, "envs": n, "steps_per_launch": T, "kernel": k,
-                      "greedy_us_per_step": round(us_g, 3), "greedy_frac_of_hbm_peak": round(alg / (us_g * 1e-6) / 6545.6e9, 4),
-                      "open_loop_per_step_out_us_per_step": round(us_o, 3),
-                      "open_loop_frac_of_hbm_peak": round(alg / (us_o * 1e-6) / 6545.6e9, 4)}), flush=True)
+    res = {"variant": variant, "envs": n, "steps_per_launch": T, "steps_per_launch_per_step_slices": T_ps, "kernel": k}
+    for name, kw, steps in (("greedy_resident", {}, T), ("greedy_per_step_slices", {"per_step": True}, T_ps),
+                            ("open_loop_resident", {"actions": acts}, T),
+                            ("open_loop_per_step_slices", {"actions": acts[:T_ps], "per_step": True}, T_ps)):
+        if "per_step" in kw:
+            kw["out"] = env.multi_step(steps, kernel=k, **kw)
+        us = timed(lambda: env.multi_step(steps, kernel=k, **kw)) * T / steps
+        res[name + "_us_per_step"] = round(us, 3)
+        res[name + "_frac_of_hbm_peak"] = round(alg / (us * 1e-6) / 6545.6e9, 4)
+        kw.pop("out", None)
+        torch.cuda.empty_cache()
+    print(json.dumps(res), flush=True)
