@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(BLOCK, (RC == 16 ? WH_MIN_BLOCKS_LARGE : RC ==
                                reinterpret_cast<float *>(StageMem<GC, RC, true>::mine(smem, g)),
                                reinterpret_cast<float *>(StageMem<GC, RC, true>::warp_area(smem)), t.env0);
     else if (P.obs.requests)
-        build_obs<GC, RC>(P, P.obs, g, e, R, s, active, tpos16, flavour, live, StageMem<GC, RC>::mine(smem, g),
+        build_obs<GC, RC, 3, GREEDY>(P, P.obs, g, e, R, s, active, tpos16, flavour, live, StageMem<GC, RC>::mine(smem, g),
                           StageMem<GC, RC>::warp_area(smem), t.env0);
 }
 
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(LOWOCC ? 64 : BLOCK, LOWOCC ? 1 : (RC == 16 ? 
             if (done) { active = a2; flavour = WH_OBS_RESET; }
         }
         if (with_obs) {
-            build_obs<GC, RC>(P, o, g, e, R, s, active, so.tpos16, flavour, t.live, StageMem<GC, RC>::mine(smem, g),
+            build_obs<GC, RC, 3, GREEDY>(P, o, g, e, R, s, active, so.tpos16, flavour, t.live, StageMem<GC, RC>::mine(smem, g),
                               StageMem<GC, RC>::warp_area(smem), t.env0);
             __syncwarp();                                                      // staging is reused by the next step
         }

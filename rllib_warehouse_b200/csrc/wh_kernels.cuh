@@ -652,6 +652,9 @@ __device__ __forceinline__ StepOut do_world(const KParams &P, const Group<GC> &g
 // registers. other_*: one environment's block of a key is assembled in shared memory and streamed
 // out with 128-bit stores (st.global.cs: written once, never re-read here).
 // Shared-memory staging area of one environment while its observation is written (compile-time R).
+#ifndef WH_COOP_FAST
+#define WH_COOP_FAST 1      // Medium copy-out: the all-environments-live fast path (tuning builds: 0)
+#endif
 #ifndef WH_COOP_MEDIUM
 #define WH_COOP_MEDIUM 1
 #endif
@@ -671,7 +674,12 @@ struct ObsStage {
 
 // PART: which keys this caller writes — bit 0: num_agents, self_*, requests; bit 1: other_* (k_multi_ws splits
 // one environment's observation between two warps; everybody else writes all of it)
-template <int GC, int RC, int PART = 3>
+// FAST (Medium copy-out only): take the all-environments-live fast path. It executes ~100 fewer instructions per
+// warp, which pays where the kernel is issue-bound — with the in-kernel solver: k_step Medium 65 536 greedy
+// 0.866 -> 0.892, k_multi 31.2 -> 29.4 us per step — and costs where it is bound by the write stream (the stores
+// of a warp then issue in one burst: k_step random actions -0.2 .. -0.8 %, k_multi open-loop per-step slices
+// -14 %), so the callers enable it for the GREEDY instantiations only (same-box A/B, profiles/README.md).
+template <int GC, int RC, int PART = 3, bool FAST = false>
 __device__ __forceinline__ void build_obs(const KParams &P, const wh_obs &o, const Group<GC> &g, env_t e, int R,
                                           const EnvRegs &s, unsigned long long active, uint32_t tpos16,
                                           int flavour, bool live, unsigned char *stage,
@@ -752,6 +760,57 @@ __device__ __forceinline__ void build_obs(const KParams &P, const wh_obs &o, con
         }
         __syncwarp();
         const int lane = g.lane;
+        // Fast path (every step of a full batch): all EPW environments of the warp are written. No liveness
+        // tests, and the request row / environment of every element follow from compile-time constants:
+        // element i = u + 32k (u = lane - mis) has row (u + 5k) mod 9 and environment i / 81.
+        constexpr uint32_t ALL_LIVE = 1u | (1u << GC) | (1u << (2 * GC));
+        if (WH_COOP_FAST && FAST && (lm & ALL_LIVE) == ALL_LIVE && !__any_sync(FULL, flavour != WH_OBS_STEP)) {
+            static_assert(EPW == 3 && RC == 9, "index arithmetic below is written for 3 x 9");
+            if constexpr ((PART & 1) != 0) {
+                constexpr int PER_ENV = RC * RC;
+                const uint32_t base4 = env0 * (uint32_t)PER_ENV;
+                const int u = lane - (int)(base4 & 1u);                         // -1 .. 31
+                const int u9 = u + 9, r0 = u9 - RC * ((u9 * 57) >> 9);          // (u + 9) mod 9
+                int4 *d = reinterpret_cast<int4 *>(o.requests) + base4 + u;
+                const int4 *src = w_req + r0;
+#pragma unroll
+                for (int k = 0; k < (EPW * PER_ENV + 1 + 31) / 32; ++k) {
+                    constexpr int K32 = 32;
+                    const int ck = (5 * k) % 9;                                 // 32k mod 9
+                    const int i = u + K32 * k;
+                    // row r0 + ck, minus 9 on wrap-around: the unsigned minimum of the two candidates
+                    const int off = (int)min((uint32_t)(r0 + ck), (uint32_t)(r0 + ck - RC)) - r0;
+                    const int env = (i >= PER_ENV) + (i >= 2 * PER_ENV);
+                    if ((k > 0 || i >= 0) && (K32 * k + 31 < EPW * PER_ENV || i < EPW * PER_ENV))
+                        WH_ST(d + K32 * k, src[env * RC + off]);
+                }
+            }
+            if constexpr ((PART & 2) == 0) return;
+            {   // other_positions [N,R,R-1,2]: staged in output order
+                int4 *d = reinterpret_cast<int4 *>(o.other_positions) + env0 * (uint32_t)ROWS4 + lane;
+                const int4 *src = reinterpret_cast<const int4 *>(w_pos) + lane;
+#pragma unroll
+                for (int k = 0; k < (EPW * ROWS4 + 31) / 32; ++k)
+                    if (32 * k + 31 < EPW * ROWS4 || lane + 32 * k < EPW * ROWS4) WH_ST(d + 32 * k, src[32 * k]);
+            }
+            if (lane < EPW * (St::ROWS / 8))   // other_availabilities [N,R,R-1]: 72 bytes per env = 9 int2
+                WH_ST(reinterpret_cast<int2 *>(o.other_availabilities + (size_t)env0 * St::ROWS) + lane,
+                      reinterpret_cast<const int2 *>(w_av)[lane]);
+            __syncwarp();
+            // core.py:428: every agent's block is the same (R-1)-row table; 8 rows = 4 int4 per env
+            if (writer) w_pos[gi * (RC - 1) + g.gl] = t_fixed;
+            __syncwarp();
+            int4 *d_t = reinterpret_cast<int4 *>(o.other_delivery_targets) + env0 * (uint32_t)ROWS4 + lane;
+            static_assert(ROWS4 % 4 == 0 && 32 % 4 == 0, "table period");
+            const int4 *tsrc = reinterpret_cast<const int4 *>(w_pos) + (lane & 3);
+#pragma unroll
+            for (int k = 0; k < (EPW * ROWS4 + 31) / 32; ++k) {
+                const int i = lane + 32 * k;
+                const int env = (i >= ROWS4) + (i >= 2 * ROWS4);
+                if (32 * k + 31 < EPW * ROWS4 || i < EPW * ROWS4) WH_ST(d_t + 32 * k, tsrc[env * ((RC - 1) / 2)]);
+            }
+            return;
+        }
         if constexpr ((PART & 1) != 0) {   // requests [N,R,R,4]: R copies of the env's R request rows (core.py:429)
             constexpr int PER_ENV = RC * RC;                                    // int4 per env
             const uint32_t base4 = env0 * (uint32_t)PER_ENV;
