@@ -652,6 +652,9 @@ __device__ __forceinline__ StepOut do_world(const KParams &P, const Group<GC> &g
 // registers. other_*: one environment's block of a key is assembled in shared memory and streamed
 // out with 128-bit stores (st.global.cs: written once, never re-read here).
 // Shared-memory staging area of one environment while its observation is written (compile-time R).
+#ifndef WH_FLAT_UNITS
+#define WH_FLAT_UNITS 1     // Small flat copy-out: per-lane fixed sources over 2-environment units (tuning builds: 0)
+#endif
 #ifndef WH_COOP_FAST
 #define WH_COOP_FAST 1      // Medium copy-out: the all-environments-live fast path (tuning builds: 0)
 #endif
@@ -1109,6 +1112,39 @@ __device__ __forceinline__ void build_obs_flat(const KParams &P, const Group<GC>
             const bool l = env_live(t);
             prefix = prefix && !(l && live_envs != t);               // a live env after a dead one: not a prefix
             live_envs += l ? 1 : 0;
+        }
+        // Small, every environment of the warp written (every step of a full batch): the warp's 8 environments are
+        // 4 UNITS of 2 (296 floats = 74 float4 = 37 whole sectors each), and float4 c of a unit has the same four
+        // sources in every unit — up to the unit's table offset, a compile-time constant once the loop is unrolled.
+        // Lane L owns float4 L, L + 32 and (L < 10) L + 64 of every unit: it fetches their 12 source addresses
+        // ONCE and then issues 4 shared-memory loads + one 128-bit store per float4 with immediate offsets
+        // (~80 instructions per lane instead of ~170 for the map-indexed loop below; the kernel is issue-bound).
+        if constexpr (RC == 4 && WH_FLAT_UNITS) {
+            if (live_envs == EPW) {
+                constexpr int UF4 = 2 * M::RF / 4;                             // float4 per unit (74)
+                constexpr int CH = (UF4 + 31) / 32;                            // float4 per lane and unit (3)
+                static_assert(EPW % 2 == 0 && (2 * M::RF) % 8 == 0, "units are whole sectors");
+                const uint16_t *wm = flat_warp_map<RC>();
+                const float *a[CH][4];
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    const int c = g.lane + 32 * j;
+                    const uint2 v = (c < UF4) ? __ldg(reinterpret_cast<const uint2 *>(wm + 4 * c)) : make_uint2(0u, 0u);
+                    a[j][0] = wstage + (v.x & 0xFFFFu); a[j][1] = wstage + (v.x >> 16);
+                    a[j][2] = wstage + (v.y & 0xFFFFu); a[j][3] = wstage + (v.y >> 16);
+                }
+                float4 *o4 = reinterpret_cast<float4 *>(wout) + g.lane;
+#pragma unroll
+                for (int u = 0; u < EPW / 2; ++u) {
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) {
+                        if (32 * j + 31 < UF4 || g.lane + 32 * j < UF4)
+                            WH_ST(o4 + u * UF4 + 32 * j, make_float4(a[j][0][u * 2 * M::VS], a[j][1][u * 2 * M::VS],
+                                                                     a[j][2][u * 2 * M::VS], a[j][3][u * 2 * M::VS]));
+                    }
+                }
+                return;
+            }
         }
         // (Large keeps the per-element map: its 9.3 KB composed table measured 3 % slower, HBM-bound either way)
         if (prefix && RC != 16) {

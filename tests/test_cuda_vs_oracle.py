@@ -639,6 +639,33 @@ def test_multi_step_greedy_equals_single_launches(size, n, p, kernel):
     assert torch.equal(one.stats, many.stats) and int(one.stats[0]) == 2 * n
 
 
+@pytest.mark.parametrize("kernel", MULTI_KERNELS)
+@pytest.mark.parametrize("size,n", [("small", 1029), ("medium", 334), ("large", 131)])
+def test_multi_step_greedy_per_step_slices_equal_single_launches(size, n, kernel):
+    """wh_multi_step with the in-kernel solver AND per-step outputs (every step's observations / rewards / dones in
+    its own [t] slice), across an episode boundary with in-kernel auto-reset: slice t == what the t-th
+    wh_greedy_step launch leaves in the resident tensors."""
+    from rllib_warehouse_b200 import VARIANTS, BatchedWarehouse
+    cfg = VARIANTS[size].replace(random_num_agents=True)
+    one = BatchedWarehouse(cfg, n, seed=77, auto_reset=True)
+    many = BatchedWarehouse(cfg, n, seed=77, auto_reset=True)
+    one.reset(); many.reset()
+    for _ in range(190):
+        one.greedy_step(random_action_prob=0.1, solver_seed=9, want_actions=False)
+    many.multi_step(190, random_action_prob=0.1, solver_seed=9, kernel=kernel)
+    T = 25                                                # steps 191 .. 215: the episode ends at 200
+    obs, rew, dones = many.multi_step(T, random_action_prob=0.1, solver_seed=9, per_step=True, kernel=kernel)
+    for t in range(T):
+        o, r, d = one.greedy_step(random_action_prob=0.1, solver_seed=9, want_actions=False)
+        assert torch.equal(rew[t], r), f"step {t}: rewards"
+        assert torch.equal(dones[t], d), f"step {t}: dones"
+        for k in gu.OBS_KEYS:
+            assert torch.equal(obs[k][t], o[k]), f"step {t}: obs {k}"
+    for k in one.state:
+        assert torch.equal(one.state[k], many.state[k]), k
+    assert torch.equal(one.stats, many.stats) and int(one.stats[0]) == n
+
+
 @pytest.mark.parametrize("keep_mb,what", [("0", "plain PLAIN kernels"), ("0.1", "half evict_last policy (KEEP = 2)"),
                                           ("1000", "full evict_last policy (KEEP = 1)")])
 def test_l2_keep_variants_are_bit_exact(keep_mb, what):
