@@ -42,6 +42,34 @@ def test_config_and_argument_validation_needs_no_gpu():
     assert b"unsupported" in L.wh_error_string(10001)
 
 
+def test_flags_match_the_header_and_multi_kernel_selection_is_validated():
+    """The Python binding's flag constants are the header's; wh_multi_step rejects an unknown kernel selection, and a
+    warp-specialised kernel without observations or for a non-variant geometry, before any CUDA call."""
+    from rllib_warehouse_b200 import LARGE, WarehouseConfig
+    from rllib_warehouse_b200 import _native as nv
+    header = open(os.path.join(ROOT, "include", "wh_b200.h")).read()
+    for name, val in (("AUTO_RESET", nv.FLAG_AUTO_RESET), ("COMPACT_IO", nv.FLAG_COMPACT_IO), ("NO_PDL", nv.FLAG_NO_PDL),
+                      ("PER_STEP_OUT", nv.FLAG_PER_STEP_OUT)):
+        m = re.search(r"#define\s+WH_FLAG_%s\s+(\d+)" % name, header)
+        assert m and int(m.group(1)) == val, name
+    assert "#define WH_FLAG_MULTI_KERNEL(k) (((k) & 7) << 4)" in header
+    assert [nv.flag_multi_kernel(k) for k in ("auto", "throughput", "low_occupancy", "ws1", "ws2")] == [0, 16, 32, 48, 64]
+    assert nv.flag_multi_kernel(None) == 0
+    L = nv.lib()
+    cfg = nv.make_config(LARGE)
+    st, ob = nv.State(), nv.Obs()
+    for f in nv.STATE_KEYS:
+        setattr(st, f, 16)                       # non-NULL dummies: validation only, nothing is launched
+    for f in nv.OBS_KEYS:
+        setattr(ob, f, 16)
+    args = lambda c, obs, flags: (C.byref(c), C.byref(st), 4, 0, 0, 3, None, 0, 0, 16, 16, None, obs, flags, None)  # noqa: E731
+    assert L.wh_multi_step(*args(cfg, C.byref(ob), 5 << 4)) == 10002                       # kernel 5 does not exist
+    assert L.wh_multi_step(*args(cfg, None, nv.flag_multi_kernel("ws2"))) == 10002          # ws kernels need obs
+    odd = nv.make_config(WarehouseConfig(6, 14, (3, 7, 11), 30, 10, 6))                     # runtime-geometry kernels
+    assert L.wh_multi_step(*args(odd, C.byref(ob), nv.flag_multi_kernel("ws1"))) == 10002
+    assert L.wh_multi_step(*args(cfg, C.byref(ob), 128)) == 10002                          # unknown flag bit
+
+
 def test_no_cpu_fallback():
     from rllib_warehouse_b200 import SMALL, BatchedWarehouse
     from rllib_warehouse_b200 import _native as nv
