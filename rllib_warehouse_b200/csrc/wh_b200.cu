@@ -45,6 +45,9 @@ namespace wh {
 #ifndef WH_WS_DIAG
 #define WH_WS_DIAG 0
 #endif
+#ifndef WH_ROLLOUT_MIN_BLOCKS
+#define WH_ROLLOUT_MIN_BLOCKS 4         // resident blocks per SM of k_rollout (Small / Medium / runtime geometries)
+#endif
 #ifndef WH_MULTI_MIN_BLOCKS
 #define WH_MULTI_MIN_BLOCKS 3           // resident 256-thread blocks per SM of the throughput k_multi (80 registers: at 5 blocks = 48 registers it spilled 200 B and ran 14 % slower)
 #endif
@@ -193,8 +196,9 @@ __global__ void __launch_bounds__(BLOCK, (RC == 16 ? WH_MIN_BLOCKS_LARGE : RC ==
 // stays in registers between the steps and no observation is materialised (the solver reads the
 // state it would have been shown). Leaves the state, the per-agent reward sums of these steps, the
 // last step's done flags and the episode statistics exactly as n_steps wh_greedy_step launches do.
-template <int GC, int RC>
-__global__ void __launch_bounds__(BLOCK, (RC == 16 ? 4 : WH_MIN_BLOCKS)) k_rollout(const __grid_constant__ KParams P) {
+// LOWOCC: launch-sized batches run 64-thread blocks spread over the SMs with no register cap (as k_multi does).
+template <int GC, int RC, bool LOWOCC = false>
+__global__ void __launch_bounds__(LOWOCC ? 64 : BLOCK, LOWOCC ? 1 : (RC == 16 ? 4 : WH_ROLLOUT_MIN_BLOCKS)) k_rollout(const __grid_constant__ KParams P) {
     const Group<GC> g(P.G);
     const Tile<GC> t(P, g);
     const int R = RC ? RC : P.R;
@@ -208,16 +212,20 @@ __global__ void __launch_bounds__(BLOCK, (RC == 16 ? 4 : WH_MIN_BLOCKS)) k_rollo
     int4 acc4 = make_int4(0, 0, 0, 0);
     bool acc_dirty = false;
     if (g.gl == 0) acc4 = reinterpret_cast<const int4 *>(P.acc)[e];
+    unsigned long long active0 = 0ull;   // the active-request mask of the current state, carried from step to step
     for (int it = 0; it < P.n_steps; ++it) {
-        unsigned long long active0;
-        const int act = greedy_from_state<GC, RC>(P, g, R, env_id, s, active0);
+        const int act = greedy_from_state<GC, RC>(P, g, R, env_id, s, active0, it > 0);
         s.time += 1;                                                           // core.py:267
         do_moves<GC, RC>(P, g, R, s.A, act, -1, false, s.pos16);
         const StepOut so = do_world(P, g, e, R, env_id, s, false, active0, true);
         ret += so.reward;
         done = s.time >= P.episode;                                            // core.py:438
         account_episode<true>(P, g.gl == 0 && t.live, e, so, s, done, auto_reset, acc4, acc_dirty);
-        if (auto_reset && __any_sync(FULL, done)) do_reset(P, g, e, R, env_id, s, false, done && t.live);
+        active0 = so.active;
+        if (auto_reset && __any_sync(FULL, done)) {
+            const unsigned long long a2 = do_reset(P, g, e, R, env_id, s, false, done && t.live);
+            if (done && t.live) active0 = a2;
+        }
     }
     if (t.live) {
         store_env(P, g, e, R, (RC ? 4 * GC : P.P), s, true);
@@ -262,10 +270,12 @@ __global__ void __launch_bounds__(LOWOCC ? 64 : BLOCK, LOWOCC ? 1 : (RC == 16 ? 
     // step's dependent chain otherwise: an L2 / HBM round trip per step)
     int act_next = -1;
     if (!GREEDY && g.gl < R) act_next = acts[e * R + g.gl];
+    unsigned long long active_cur = 0ull;   // GREEDY: the active-request mask of the current state, carried from step to step
+    constexpr bool CARRY = LOWOCC || RC != 16;   // (the 80-register Large throughput kernel would spill the two registers)
     for (int it = 0; it < P.n_steps; ++it) {
         int act = -1;
-        unsigned long long active0 = 0ull;
-        if (GREEDY) act = greedy_from_state<GC, RC>(P, g, R, env_id, s, active0);
+        unsigned long long active0 = active_cur;
+        if (GREEDY) act = greedy_from_state<GC, RC>(P, g, R, env_id, s, active0, CARRY && it > 0);
         else {
             act = act_next;
             acts += NR;
@@ -288,6 +298,7 @@ __global__ void __launch_bounds__(LOWOCC ? 64 : BLOCK, LOWOCC ? 1 : (RC == 16 ? 
             const unsigned long long a2 = do_reset(P, g, e, R, env_id, s, false, done && t.live);
             if (done) { active = a2; flavour = WH_OBS_RESET; }
         }
+        active_cur = (done && !t.live) ? so.active : active;   // (do_reset leaves the state of a dead lane's env alone)
         if (with_obs) {
             build_obs<GC, RC, 3, GREEDY>(P, o, g, e, R, s, active, so.tpos16, flavour, t.live, StageMem<GC, RC>::mine(smem, g),
                               StageMem<GC, RC>::warp_area(smem), t.env0);
@@ -335,10 +346,11 @@ __device__ __forceinline__ void named_bar_sync(int id, int n) {
 __device__ __forceinline__ void named_bar_arrive(int id, int n) {
     if (id == 1) named_bar_arrive_i<1>(n); else if (id == 2) named_bar_arrive_i<2>(n); else if (id == 3) named_bar_arrive_i<3>(n); else named_bar_arrive_i<4>(n);
 }
-// the arrive that frees a ring slot: `dep` = a value loaded from the slot, so the load has completed
-__device__ __forceinline__ void named_bar_arrive_after(int id, int n, uint32_t dep) {
-    asm volatile("{\n\t.reg .b32 t;\n\tmov.b32 t, %0;\n\t}" ::"r"(dep) : "memory");
-    named_bar_arrive(id, n);
+// The arrive that frees a ring slot must not be issued before the slot has been READ. `w0` is the first word loaded
+// from the slot; its bit 31 is never set (cell 16 | target 8 | agent count 6 | flavour 1 bits), so the thread count
+// below always equals n — but only the loaded value says so, which makes the arrive data-dependent on the load.
+__device__ __forceinline__ void named_bar_arrive_after(int id, int n, uint32_t w0) {
+    named_bar_arrive(id, n + (int)(w0 >> 31));
 }
 
 template <int GC, int RC, int PART>
@@ -354,7 +366,7 @@ __device__ __forceinline__ void multi_ws_obs_loop(const KParams &P, const Group<
         const int b = it & 1;
         named_bar_sync(1 + b, nthreads);                                        // full[b]
         const uint4 h = ring[b][g.lane];
-        if (it + 2 < T) named_bar_arrive_after(3 + b, nthreads, h.x ^ h.y ^ h.z ^ h.w);   // empty[b]
+        if (it + 2 < T) named_bar_arrive_after(3 + b, nthreads, h.x);                      // empty[b]
         EnvRegs s;
         s.pos16 = h.x & 0xFFFFu;
         s.atgt = (int)(int8_t)((h.x >> 16) & 0xFFu);
@@ -413,10 +425,11 @@ __global__ void __launch_bounds__(32 * (1 + NOBS)) k_multi_ws(const __grid_const
     // step's dependent chain otherwise: an L2 / HBM round trip per step)
     int act_next = -1;
     if (!GREEDY && g.gl < R) act_next = acts[e * R + g.gl];
+    unsigned long long active_cur = 0ull;   // GREEDY: the active-request mask of the current state, carried from step to step
     for (int it = 0; it < P.n_steps; ++it) {
         int act = -1;
-        unsigned long long active0 = 0ull;
-        if (GREEDY) act = greedy_from_state<GC, RC>(P, g, R, env_id, s, active0);
+        unsigned long long active0 = active_cur;
+        if (GREEDY) act = greedy_from_state<GC, RC>(P, g, R, env_id, s, active0, it > 0);
         else {
             act = act_next;
             acts += NR;
@@ -436,6 +449,7 @@ __global__ void __launch_bounds__(32 * (1 + NOBS)) k_multi_ws(const __grid_const
         // the hand-over comes first: everything after it is off the observation warps' critical path
         const bool resets = auto_reset && __any_sync(FULL, done);
         if (!resets) {
+            active_cur = active;
             const int b = it & 1;
             if (it >= 2) named_bar_sync(3 + b, NT);                             // empty[b]
             ring[b][g.lane] = make_uint4((s.pos16 & 0xFFFFu) | (((uint32_t)s.atgt & 0xFFu) << 16) | ((uint32_t)s.A << 24),
@@ -452,6 +466,7 @@ __global__ void __launch_bounds__(32 * (1 + NOBS)) k_multi_ws(const __grid_const
         if (resets) {
             const unsigned long long a2 = do_reset(P, g, e, R, env_id, s, false, done && t.live);
             if (done) { active = a2; flav = 1u; }
+            active_cur = (done && !t.live) ? so.active : active;   // (do_reset leaves the state of a dead lane's env alone)
             const int b = it & 1;
             if (it >= 2) named_bar_sync(3 + b, NT);                             // empty[b]
             ring[b][g.lane] = make_uint4((s.pos16 & 0xFFFFu) | (((uint32_t)s.atgt & 0xFFu) << 16) | ((uint32_t)s.A << 24) | (flav << 30),
@@ -728,7 +743,13 @@ static void launch_kind(Kind kind, const KParams &K, cudaStream_t s) {
     case K_RESET: k_reset<GC, RC><<<grid, BLOCK, 0, s>>>(K); break;
     case K_OBS: k_obs<GC, RC><<<grid, BLOCK, 0, s>>>(K); break;
     case K_OBS_FLAT: k_obs_flat<GC, RC><<<grid, BLOCK, 0, s>>>(K); break;
-    case K_ROLLOUT: k_rollout<GC, RC><<<grid, BLOCK, 0, s>>>(K); break;
+    case K_ROLLOUT: {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+        if (warps < (long long)sms * 16) k_rollout<GC, RC, true><<<(unsigned)((warps + 1) / 2), 64, 0, s>>>(K);
+        else k_rollout<GC, RC><<<grid, BLOCK, 0, s>>>(K);
+        break;
+    }
     case K_MULTI:
     case K_GMULTI: {
         // launch-sized batches: with fewer warps than the GPU has schedulers, spread them over the SMs

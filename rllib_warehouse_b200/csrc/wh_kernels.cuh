@@ -1333,12 +1333,16 @@ __device__ __forceinline__ unsigned long long do_reset(const KParams &P, const G
 // (core.py:233-236), so agents head for the map centre; otherwise a free agent goes to the
 // L1-nearest request (first minimum in request order == ascending pickup index), a delivering
 // agent to its delivery cell.
+// active_io: out = the active-request mask of this state (do_world derives the post-step mask from it); with
+// have_active it is also an INPUT — the multi-step loops pass the mask the previous step left (StepOut::active,
+// or do_reset's) instead of gathering it from the lanes again.
 template <int GC, int RC>
 __device__ __forceinline__ int greedy_from_state(const KParams &P, const Group<GC> &g, int R,
-                                                 uint32_t env_id, const EnvRegs &s, unsigned long long &active_out) {
+                                                 uint32_t env_id, const EnvRegs &s, unsigned long long &active_io,
+                                                 bool have_active = false) {
     const Geo<GC> geo(P);
-    const unsigned long long active = active_mask(g, s.pt4);
-    active_out = active;                             // do_world derives the post-step mask from it
+    const unsigned long long active = have_active ? active_io : active_mask(g, s.pt4);
+    active_io = active;
     const int px = s.pos16 & 0xFF, py = s.pos16 >> 8;
     // lane r takes the r-th active pickup point's cell
     const int nact = __popcll(active);

@@ -545,7 +545,9 @@ def test_masked_reset_and_desynchronised_episodes(size, n):
     assert np.array_equal(gpu.stats.cpu().numpy(), cpu.stats)
 
 
-@pytest.mark.parametrize("size,n,p", [("small", 4097, 0.0), ("medium", 1000, 0.25), ("large", 515, 0.0)])
+@pytest.mark.parametrize("size,n,p", [("small", 4097, 0.0), ("medium", 1000, 0.25), ("large", 515, 0.0),
+                                      # batches past the launch-sized threshold: the 256-thread-block instantiation
+                                      ("small", 19001, 0.1), ("medium", 7200, 0.0), ("large", 4801, 0.05)])
 def test_multi_step_greedy_rollout_kernel(size, n, p):
     """wh_greedy_rollout: T solver+step iterations in one launch (state in registers, no per-step
     observations) == T wh_greedy_step launches: state, statistics, dones, reward sums; across two
