@@ -45,11 +45,16 @@ typedef uint32_t env_t;
 #ifndef WH_KEEP_MAX_MB
 #define WH_KEEP_MAX_MB 32
 #endif
+#ifndef WH_KEEP_PART_FRAC
+#define WH_KEEP_PART_FRAC 0.5   // share of the state accesses that get evict_last under the partial policy (KEEP = 2)
+#endif
+#define WH_STR2(x) #x
+#define WH_STR(x) WH_STR2(x)
 // KEEP levels: 0 = plain accesses, 1 = every state access evict_last, 2 = half of them (fractional policy)
 template <int KEEP>
 __device__ __forceinline__ uint64_t l2_evict_last() {
     uint64_t p;
-    if constexpr (KEEP == 2) asm("createpolicy.fractional.L2::evict_last.b64 %0, 0.5;" : "=l"(p));
+    if constexpr (KEEP == 2) asm("createpolicy.fractional.L2::evict_last.b64 %0, " WH_STR(WH_KEEP_PART_FRAC) ";" : "=l"(p));
     else asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
