@@ -53,6 +53,9 @@ def parse():
     ap.add_argument("--envs", type=int, default=262144, help="envs per GPU (weak, default) / total envs (strong)")
     ap.add_argument("--scaling", default="weak", choices=["strong", "weak"])
     ap.add_argument("--policy", default="random", choices=["random", "greedy", "greedy_fused"])
+    ap.add_argument("--action-pool", type=int, default=200,
+                    help="distinct random action tensors cycled through (200: every step's actions come from HBM; "
+                         "1 is a diagnostic: the actions stay in L2, as a just-evaluated policy's output would)")
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--e2e-chunks", type=int, default=None,
                     help="wh_env_create n_chunks for every e2e leg (k > 0: k-chunk copy pipeline, 0: direct); "
@@ -186,6 +189,7 @@ def workload_config(args, world):
         "step": "one env.step of every env: fused move/collision/expiry/pickup/respawn/delivery + observation build",
         "l2": "observations written per step (2.2 GB per GPU for large) exceed the 126 MB L2; no flush needed",
         "parallelism": f"env-sharded x{world}, no per-step communication",
+        **({"action_pool": args.action_pool} if getattr(args, "action_pool", 200) != 200 else {}),
     }
 
 
@@ -272,7 +276,7 @@ def run_b200(args):
     R = env.R
     gen = torch.Generator(device=dev)
     gen.manual_seed(args.seed + rank)
-    n_pool = 200 if args.policy == "random" else 1
+    n_pool = max(1, args.action_pool) if args.policy == "random" else 1
     pool = [torch.randint(0, 9, (n_local, R), dtype=torch.int32, device=dev, generator=gen) for _ in range(n_pool)]
 
     launches_per_step = {"random": 1, "greedy": 2, "greedy_fused": 1}[args.policy]

@@ -51,6 +51,29 @@ namespace wh {
 #ifndef WH_MULTI_MIN_BLOCKS
 #define WH_MULTI_MIN_BLOCKS 3           // resident 256-thread blocks per SM of the throughput k_multi (80 registers: at 5 blocks = 48 registers it spilled 200 B and ran 14 % slower)
 #endif
+// Open-loop actions arrive from HBM (nobody has just written them) as small reads mixed into the step's write
+// stream. WH_ACT_BURST_*: the blocks of the first wave prefetch the step's whole action tensor into L2 in one
+// burst while they are parked in front of griddepcontrol.wait — the previous step is draining, the DRAM is
+// nearly idle, and a prefetch is only a hint (L2 is the coherence point: it cannot expose stale data). Same-box
+// A/B at 262 144 envs (profiles/README.md): Small 0.872 -> 0.895 of the HBM peak (its 4 MB of actions survive
+// the 143 MB of observations a step writes), Medium 0.960 -> 0.952, Large 0.989 -> 0.983 — on for Small only.
+// Rejected variants of the same idea: every warp prefetching the actions of the warp one (0.5, 2) wave(s) ahead
+// (Small 0.869), the burst with the evict_last priority (Small 0.834), evict_first on the action loads.
+#ifndef WH_ACT_BURST_SMALL
+#define WH_ACT_BURST_SMALL 1
+#endif
+#ifndef WH_ACT_BURST_OTHER
+#define WH_ACT_BURST_OTHER 0
+#endif
+#ifndef WH_ACT_BURST_MAX_MB
+#define WH_ACT_BURST_MAX_MB 8           // lines beyond this would be evicted again before their warp arrives
+#endif
+#ifndef WH_KEEP_PART_LARGE
+#define WH_KEEP_PART_LARGE 0            // tuning builds: the partial evict_last policy (KEEP = 2) for Large as well
+#endif
+#ifndef WH_KEEP_PART_MAX_MB
+#define WH_KEEP_PART_MAX_MB (2 * WH_KEEP_MAX_MB)
+#endif
 constexpr int BLOCK = WH_BLOCK;   // threads per block (tuning: -DWH_BLOCK / -DWH_MIN_BLOCKS)
 
 // ---------------------------------------------------------------------------------------------
@@ -124,7 +147,7 @@ __device__ __forceinline__ void account_episode(const KParams &P, bool owner, en
 // auto-reset) — core.py:262-442, solvers.py:27-58
 // PLAIN: the caller passes int32 actions / float32 rewards, no dict order and no replayed draws (the
 // throughput path); the instantiation then carries none of the code or tests for those options.
-// KEEP (PLAIN only): the state is loaded / stored with the L2 evict_last priority (1 = all accesses, 2 = half),
+// KEEP (PLAIN only): the state is loaded / stored with the L2 evict_last priority (1 = all accesses, 2 = all arrays but the timers),
 // see wh_kernels.cuh.
 template <int GC, int RC, bool GREEDY, bool FLAT, bool PLAIN = false, int KEEP = 0>
 __global__ void __launch_bounds__(BLOCK, (RC == 16 ? WH_MIN_BLOCKS_LARGE : RC == 9 ? WH_MIN_BLOCKS_MEDIUM : RC == 4 ? WH_MIN_BLOCKS_SMALL : WH_MIN_BLOCKS)) k_step(const __grid_constant__ KParams P) {
@@ -139,6 +162,20 @@ __global__ void __launch_bounds__(BLOCK, (RC == 16 ? WH_MIN_BLOCKS_LARGE : RC ==
     const env_t e = t.e;
     const uint32_t env_id = (uint32_t)P.env_id0 + e;
     EnvRegs s;
+    if constexpr ((RC == 4 ? WH_ACT_BURST_SMALL : WH_ACT_BURST_OTHER) != 0 && PLAIN && !GREEDY && RC != 0) {
+        // burst prefetch of this step's actions by the first wave (see WH_ACT_BURST_*); not for host-resident
+        // (zero-copy) actions, whose launches carry WH_FLAG_NO_PDL
+        constexpr uint32_t MIN_BLOCKS = RC == 16 ? WH_MIN_BLOCKS_LARGE : RC == 9 ? WH_MIN_BLOCKS_MEDIUM : WH_MIN_BLOCKS_SMALL;
+        constexpr uint32_t WAVE_BLOCKS = 148 * MIN_BLOCKS;
+        if (blockIdx.x < WAVE_BLOCKS && !(P.flags & WH_FLAG_NO_PDL)) {
+            const uintptr_t a = (uintptr_t)P.actions, a_al = a & ~(uintptr_t)127;
+            size_t lines = (a + (size_t)P.N * (RC * 4) - a_al + 127) >> 7;
+            if (lines > ((size_t)WH_ACT_BURST_MAX_MB << 13)) lines = (size_t)WH_ACT_BURST_MAX_MB << 13;
+            const uint32_t nthreads = (gridDim.x < WAVE_BLOCKS ? gridDim.x : WAVE_BLOCKS) * BLOCK;
+            for (size_t line = (size_t)blockIdx.x * BLOCK + threadIdx.x; line < lines; line += nthreads)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a_al + line * 128));
+        }
+    }
     asm volatile("griddepcontrol.wait;" ::: "memory");
     load_env<GC, KEEP>(P, g, e, R, (RC ? 4 * GC : P.P), s);
     int4 acc4 = make_int4(0, 0, 0, 0);
@@ -710,6 +747,9 @@ static void launch_kind(Kind kind, const KParams &K, cudaStream_t s) {
             cudaFuncSetAttribute(k_step<GC, RC, true, false, RC != 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
             cudaFuncSetAttribute(k_step<GC, RC, false, false, RC != 0, (RC != 0 ? 1 : 0)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
             cudaFuncSetAttribute(k_step<GC, RC, true, false, RC != 0, (RC != 0 ? 1 : 0)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+            constexpr int KP = (RC == 16 && WH_KEEP_PART_LARGE) ? 2 : (RC != 0 ? 1 : 0);   // the partial-policy instantiation, where it exists
+            cudaFuncSetAttribute(k_step<GC, RC, false, false, RC != 0, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+            cudaFuncSetAttribute(k_step<GC, RC, true, false, RC != 0, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
             done[dev].store(true, std::memory_order_release);
         }
     }
@@ -717,10 +757,11 @@ static void launch_kind(Kind kind, const KParams &K, cudaStream_t s) {
     // KEEP variant: the whole state of this launch (narrow state + episode counters) fits the keep budget
     const double state_mb = (double)K.N * (3.0 * K.R + 3.0 * K.P + 9.0 + 16.0) / 1048576.0;
     static const double keep_mb = [] { const char *v = getenv("WH_B200_KEEP_MB"); return v ? atof(v) : (double)WH_KEEP_MAX_MB; }();
-    // level 1 while the state fits the budget; Medium also pays at level 2 (half) up to twice the budget
-    const int keep = !(plain && (RC == 9 || RC == 16)) ? 0 : state_mb <= keep_mb ? 1 : (RC == 9 && state_mb <= 2 * keep_mb) ? 2 : 0;
+    // level 1 while the state fits the budget; Medium also pays at level 2 (all but the timers) up to twice the budget
+    constexpr bool PART = RC == 9 || (RC == 16 && WH_KEEP_PART_LARGE);
+    const int keep = !(plain && (RC == 9 || RC == 16)) ? 0 : state_mb <= keep_mb ? 1 : (PART && state_mb <= keep_mb * ((double)WH_KEEP_PART_MAX_MB / WH_KEEP_MAX_MB)) ? 2 : 0;
     constexpr bool KV = RC == 9 || RC == 16;      // the KEEP instantiations exist for Medium and Large only
-    constexpr int K1 = KV ? 1 : 0, K2 = RC == 9 ? 2 : 0;
+    constexpr int K1 = KV ? 1 : 0, K2 = PART ? 2 : 0;
     switch (kind) {
     case K_STEP:
         if (keep == 2) launch_step(k_step<GC, RC, false, false, KV, K2>, grid, dyn, s, K);

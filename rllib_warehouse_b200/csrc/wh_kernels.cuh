@@ -38,9 +38,14 @@ typedef uint32_t env_t;
 // 0.966 -> 1.004. It costs L2 capacity the write-back path also wants, so it only pays while the state is
 // small against L2: at 262 144 envs (37 / 64 MB) it is -0.4 % / -1.3 %, and Small (whose 143 MB observation
 // stream leaves the state in L2 anyway) loses 3.6 %. A FRACTIONAL policy (half of the accesses evict_last)
-// still pays for Medium at 37 MB (0.923 -> 0.939) but not for Large at 64 MB (-0.6 .. -1.5 %). Hence
-// compile-time variants of the throughput (PLAIN) kernels — KEEP = 1 (all) / 2 (half) — that the launcher
-// selects from the state size (WH_KEEP_MAX_MB, and twice that for the half policy of Medium). Observation
+// still pays for Medium at 37 MB (0.923 -> 0.939) but not for Large at 64 MB (-0.6 .. -1.5 %). Choosing the
+// part BY ARRAY instead of at random is better again (Medium 262 144 envs 0.928 -> 0.950 / 0.960 on two boxes,
+// with the in-kernel solver 0.921 -> 0.945): with a random half nearly every warp still has some load that
+// misses, with "everything except the timers" (55 % of the bytes) the loads a warp needs FIRST always hit
+// and the timers — first used after the move loop — arrive behind it. Dropping pickup_tgt as well: 0.936;
+// the same for Large (all but the timers, or also without pickup_tgt): 0.965 / 0.977 vs 0.977 plain. Hence
+// compile-time variants of the throughput (PLAIN) kernels — KEEP = 1 (all) / 2 (part) — that the launcher
+// selects from the state size (WH_KEEP_MAX_MB, and twice that for the partial policy of Medium). Observation
 // stores with evict_first were measured too: -4 % everywhere, not used.
 #ifndef WH_KEEP_MAX_MB
 #define WH_KEEP_MAX_MB 32
@@ -50,14 +55,22 @@ typedef uint32_t env_t;
 #endif
 #define WH_STR2(x) #x
 #define WH_STR(x) WH_STR2(x)
-// KEEP levels: 0 = plain accesses, 1 = every state access evict_last, 2 = half of them (fractional policy)
+// How KEEP = 2 picks its part of the state. 0 = a random share (WH_KEEP_PART_FRAC) of all accesses; 1 (shipped) =
+// every array except the timers (45 % of the bytes, first used after the move loop); 2 = also without pickup_tgt
+#ifndef WH_KEEP_PART_MODE
+#define WH_KEEP_PART_MODE 1
+#endif
+// KEEP levels: 0 = plain accesses, 1 = every state access evict_last, 2 = part of them (see WH_KEEP_PART_MODE)
 template <int KEEP>
 __device__ __forceinline__ uint64_t l2_evict_last() {
     uint64_t p;
-    if constexpr (KEEP == 2) asm("createpolicy.fractional.L2::evict_last.b64 %0, " WH_STR(WH_KEEP_PART_FRAC) ";" : "=l"(p));
+    if constexpr (KEEP == 2 && WH_KEEP_PART_MODE == 0) asm("createpolicy.fractional.L2::evict_last.b64 %0, " WH_STR(WH_KEEP_PART_FRAC) ";" : "=l"(p));
     else asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
+// BIG: 1 = the timers, 2 = pickup_tgt, 0 = everything else
+template <int KEEP, int BIG>
+struct KeepThis { static constexpr bool value = KEEP != 0 && !(KEEP == 2 && WH_KEEP_PART_MODE != 0 && BIG != 0 && BIG <= WH_KEEP_PART_MODE); };
 
 template <typename T>
 __device__ __forceinline__ void st_hint(T *p, const T &v, uint64_t pol) {
@@ -110,14 +123,14 @@ __device__ __forceinline__ T ld_hint(const T *p, uint64_t pol) {
 }
 
 // state accessors
-template <int KEEP, typename T>
+template <int KEEP, int BIG = 0, typename T>
 __device__ __forceinline__ T ld_state(const T *p) {
-    if constexpr (KEEP != 0) return ld_hint(p, l2_evict_last<KEEP>());
+    if constexpr (KeepThis<KEEP, BIG>::value) return ld_hint(p, l2_evict_last<KEEP>());
     else return *p;
 }
-template <int KEEP, typename T>
+template <int KEEP, int BIG = 0, typename T>
 __device__ __forceinline__ void st_state(T *p, const T &v) {
-    if constexpr (KEEP != 0) st_hint(p, v, l2_evict_last<KEEP>());
+    if constexpr (KeepThis<KEEP, BIG>::value) st_hint(p, v, l2_evict_last<KEEP>());
     else *p = v;
 }
 
@@ -425,8 +438,8 @@ __device__ __forceinline__ void load_env(const KParams &P, const Group<GC> &g, e
     s.pt4 = 0xFFFFFFFFu;
     s.tmr = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
     if (4 * g.gl < PP) {
-        s.pt4 = ld_state<KEEP>(reinterpret_cast<const uint32_t *>(P.pickup_tgt + e * PP) + g.gl);
-        s.tmr = ld_state<KEEP>(reinterpret_cast<const uint2 *>(P.pickup_timer + e * PP) + g.gl);
+        s.pt4 = ld_state<KEEP, 2>(reinterpret_cast<const uint32_t *>(P.pickup_tgt + e * PP) + g.gl);
+        s.tmr = ld_state<KEEP, 1>(reinterpret_cast<const uint2 *>(P.pickup_timer + e * PP) + g.gl);
     }
 }
 
@@ -438,8 +451,8 @@ __device__ __forceinline__ void store_env(const KParams &P, const Group<GC> &g, 
         st_state<KEEP>(P.agent_tgt + e * R + g.gl, (int8_t)s.atgt);
     }
     if (4 * g.gl < PP) {
-        st_state<KEEP>(reinterpret_cast<uint32_t *>(P.pickup_tgt + e * PP) + g.gl, s.pt4);
-        st_state<KEEP>(reinterpret_cast<uint2 *>(P.pickup_timer + e * PP) + g.gl, s.tmr);
+        st_state<KEEP, 2>(reinterpret_cast<uint32_t *>(P.pickup_tgt + e * PP) + g.gl, s.pt4);
+        st_state<KEEP, 1>(reinterpret_cast<uint2 *>(P.pickup_timer + e * PP) + g.gl, s.tmr);
     }
     if (g.gl == 0) {
         st_state<KEEP>(P.time + e, s.time);

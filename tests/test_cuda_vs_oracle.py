@@ -668,11 +668,11 @@ def test_multi_step_greedy_per_step_slices_equal_single_launches(size, n, kernel
     assert torch.equal(one.stats, many.stats) and int(one.stats[0]) == n
 
 
-@pytest.mark.parametrize("keep_mb,what", [("0", "plain PLAIN kernels"), ("0.1", "half evict_last policy (KEEP = 2)"),
+@pytest.mark.parametrize("keep_mb,what", [("0", "plain PLAIN kernels"), ("0.1", "partial evict_last policy: every state array but the timers (KEEP = 2)"),
                                           ("1000", "full evict_last policy (KEEP = 1)")])
 def test_l2_keep_variants_are_bit_exact(keep_mb, what):
     """The throughput kernels exist in three L2-policy variants for the state accesses (plain / evict_last /
-    half evict_last), selected from the state size (WH_KEEP_MAX_MB; WH_B200_KEEP_MB overrides, read once per
+    evict_last for every array but the timers), selected from the state size (WH_KEEP_MAX_MB; WH_B200_KEEP_MB overrides, read once per
     process — hence a subprocess). All three must give the oracle's results: Medium and Large, random actions
     and the in-kernel solver, flat observations, across an episode boundary."""
     import os
