@@ -58,7 +58,8 @@ namespace wh {
 // A/B at 262 144 envs (profiles/README.md): Small 0.872 -> 0.895 of the HBM peak (its 4 MB of actions survive
 // the 143 MB of observations a step writes), Medium 0.960 -> 0.952, Large 0.989 -> 0.983 — on for Small only.
 // Rejected variants of the same idea: every warp prefetching the actions of the warp one (0.5, 2) wave(s) ahead
-// (Small 0.869), the burst with the evict_last priority (Small 0.834), evict_first on the action loads.
+// (Small 0.869), the burst with the evict_last priority (Small 0.834), evict_first on the action loads, and a
+// burst that also covers the state of the first 20 / 50 % of the envs (0.884 / 0.879 vs 0.894: it is still in L2).
 #ifndef WH_ACT_BURST_SMALL
 #define WH_ACT_BURST_SMALL 1
 #endif
@@ -67,6 +68,9 @@ namespace wh {
 #endif
 #ifndef WH_ACT_BURST_MAX_MB
 #define WH_ACT_BURST_MAX_MB 8           // lines beyond this would be evicted again before their warp arrives
+#endif
+#ifndef WH_KEEP_SMALL
+#define WH_KEEP_SMALL 0                 // tuning builds: KEEP level (2 / 3) of the Small throughput kernels (0.882 / 0.886 vs 0.894 plain)
 #endif
 #ifndef WH_KEEP_PART_LARGE
 #define WH_KEEP_PART_LARGE 0            // tuning builds: the partial evict_last policy (KEEP = 2) for Large as well
@@ -762,9 +766,11 @@ static void launch_kind(Kind kind, const KParams &K, cudaStream_t s) {
     const int keep = !(plain && (RC == 9 || RC == 16)) ? 0 : state_mb <= keep_mb ? 1 : (PART && state_mb <= keep_mb * ((double)WH_KEEP_PART_MAX_MB / WH_KEEP_MAX_MB)) ? 2 : 0;
     constexpr bool KV = RC == 9 || RC == 16;      // the KEEP instantiations exist for Medium and Large only
     constexpr int K1 = KV ? 1 : 0, K2 = PART ? 2 : 0;
+    constexpr int KSM = RC == 4 ? WH_KEEP_SMALL : 0;
     switch (kind) {
     case K_STEP:
-        if (keep == 2) launch_step(k_step<GC, RC, false, false, KV, K2>, grid, dyn, s, K);
+        if (KSM && plain) launch_step(k_step<GC, RC, false, false, RC != 0, KSM>, grid, dyn, s, K);
+        else if (keep == 2) launch_step(k_step<GC, RC, false, false, KV, K2>, grid, dyn, s, K);
         else if (keep) launch_step(k_step<GC, RC, false, false, KV, K1>, grid, dyn, s, K);
         else if (plain) launch_step(k_step<GC, RC, false, false, RC != 0>, grid, dyn, s, K);
         else launch_step(k_step<GC, RC, false, false>, grid, dyn, s, K);

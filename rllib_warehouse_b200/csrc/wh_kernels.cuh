@@ -60,7 +60,8 @@ typedef uint32_t env_t;
 #ifndef WH_KEEP_PART_MODE
 #define WH_KEEP_PART_MODE 1
 #endif
-// KEEP levels: 0 = plain accesses, 1 = every state access evict_last, 2 = part of them (see WH_KEEP_PART_MODE)
+// KEEP levels: 0 = plain accesses, 1 = every state access evict_last, 2 = part of them (see WH_KEEP_PART_MODE),
+// 3 = every array except the timers and pickup_tgt (tuning builds)
 template <int KEEP>
 __device__ __forceinline__ uint64_t l2_evict_last() {
     uint64_t p;
@@ -70,7 +71,7 @@ __device__ __forceinline__ uint64_t l2_evict_last() {
 }
 // BIG: 1 = the timers, 2 = pickup_tgt, 0 = everything else
 template <int KEEP, int BIG>
-struct KeepThis { static constexpr bool value = KEEP != 0 && !(KEEP == 2 && WH_KEEP_PART_MODE != 0 && BIG != 0 && BIG <= WH_KEEP_PART_MODE); };
+struct KeepThis { static constexpr bool value = (KEEP == 1 || KEEP == 2) ? !(KEEP == 2 && WH_KEEP_PART_MODE != 0 && BIG != 0 && BIG <= WH_KEEP_PART_MODE) : (KEEP == 3 && BIG == 0); };
 
 template <typename T>
 __device__ __forceinline__ void st_hint(T *p, const T &v, uint64_t pol) {
